@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Pin the oracle against the reference and write the golden fixtures (build-container only).
+
+Runs the UNMODIFIED reference classes from /root/reference/src (behind oracle/pin/np1shim.py) on
+small seeded inputs with injected initial state, checks that the oracle restatement reproduces
+them to ~1e-10, and stores inputs + reference outputs as tests/golden/<case>.npz.  The GPU box
+has no /root/reference: tests only ever read the committed .npz files.
+
+    python oracle/pin/make_golden.py            # regenerate everything
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import np1shim  # noqa: F401,E402  (must precede the reference import)
+
+sys.path.append('/root/reference/src')
+warnings.simplefilter('ignore')
+
+from bss.ilrma import GaussILRMA, tILRMA  # noqa: E402
+from bss.iva import AuxLaplaceIVA, AuxGaussIVA  # noqa: E402
+from bss.mnmf import FastMultichannelISNMF  # noqa: E402
+from algorithm.nmf import EUCNMF, KLNMF, ISNMF, tNMF, CauchyNMF  # noqa: E402
+from algorithm.projection_back import projection_back  # noqa: E402
+from utils.utils_linalg import parallel_sort  # noqa: E402
+
+from oracle import core, ilrma, auxiva, fastmnmf, nmf, synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+TOL = 1e-9
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def check(name, got, want, tol=TOL):
+    for k in want:
+        e = rel(got[k], want[k])
+        assert e < tol, "{}: oracle deviates from the reference on '{}' (rel {:.3e})".format(name, k, e)
+
+
+def save(name, meta, inputs, outputs):
+    arrays = {'in_' + k: v for k, v in inputs.items()}
+    arrays.update({'out_' + k: v for k, v in outputs.items()})
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), meta=json.dumps(meta), **arrays)
+    print("  wrote {:<40s} {}".format(name, {k: tuple(np.shape(v)) for k, v in outputs.items()}))
+
+
+# ------------------------------------------------------------------------------- ILRMA
+
+def case_ilrma(name, C, F, T, K, spatial, norm, domain, iters, partitioning=False, seed=0):
+    X = synth.mix2(C, F, T, K=2, seed=seed)
+    W0, T0, V0 = synth.initial_state(C, F, T, K, seed=7)
+    rng = np.random.default_rng(11)
+    presets = {'demix_filter': W0}
+    opre = {'W': W0}
+    if partitioning:
+        T0 = rng.random((F, K)).astype(np.float32).astype(np.float64)
+        V0 = rng.random((K, T)).astype(np.float32).astype(np.float64)
+        Z0 = rng.random((C, K)) + 0.5
+        Z0 = (Z0 / Z0.sum(axis=0)).astype(np.float32).astype(np.float64)
+        presets['latent'] = Z0
+        opre['Z'] = Z0
+    presets.update(basis=T0, activation=V0)
+    opre.update(T=T0, V=V0)
+
+    model = GaussILRMA(n_basis=K, domain=domain, partitioning=partitioning, normalize=norm,
+                       algorithm_spatial=spatial)
+    out = model(X, iteration=iters, **presets)
+    want = {'output': out, 'basis': model.basis, 'activation': model.activation,
+            'demix_filter': model.demix_filter, 'loss': np.array(model.loss)}
+    if partitioning:
+        want['latent'] = model.latent
+
+    o_out, st, o_loss = ilrma.run(X, iteration=iters, n_basis=K, spatial=spatial, domain=domain,
+                                  normalize_mode=norm, partitioning=partitioning, **opre)
+    got = {'output': o_out, 'basis': st['T'], 'activation': st['V'],
+           'demix_filter': st['W'] if st['W'] is not None else st['W_final'], 'loss': np.array(o_loss)}
+    if partitioning:
+        got['latent'] = st['Z']
+    tol = TOL if spatial not in ('IP2', 'pairwise') else 1e-7
+    check(name, got, want, tol)
+    meta = dict(model='GaussILRMA', n_basis=K, domain=domain, partitioning=partitioning, normalize=norm,
+                algorithm_spatial=spatial, iteration=iters)
+    inputs = {'X': X, 'W0': W0, 'T0': T0, 'V0': V0}
+    if partitioning:
+        inputs['Z0'] = Z0
+    save(name, meta, inputs, want)
+
+
+def case_tilrma(name, C, F, T, K, nu, iters):
+    X = synth.mix2(C, F, T, K=2, seed=1)
+    W0, T0, V0 = synth.initial_state(C, F, T, K, seed=7)
+    model = tILRMA(n_basis=K, nu=nu)
+    out = model(X, iteration=iters, demix_filter=W0, basis=T0, activation=V0)
+    want = {'output': out, 'basis': model.basis, 'activation': model.activation,
+            'demix_filter': model.demix_filter, 'loss': np.array(model.loss)}
+    o_out, st, o_loss = ilrma.t_run(X, iteration=iters, n_basis=K, nu=nu, W=W0, T=T0, V=V0)
+    check(name, {'output': o_out, 'basis': st['T'], 'activation': st['V'], 'demix_filter': st['W'],
+                 'loss': np.array(o_loss)}, want)
+    save(name, dict(model='tILRMA', n_basis=K, nu=nu, iteration=iters),
+         {'X': X, 'W0': W0, 'T0': T0, 'V0': V0}, want)
+
+
+# ------------------------------------------------------------------------------- AuxIVA
+
+def case_auxiva(name, kind, C, F, T, spatial, iters):
+    X = synth.mix2(C, F, T, K=2, seed=2)
+    W0 = np.tile(np.eye(C, dtype=np.complex128), (F, 1, 1))
+    cls = AuxLaplaceIVA if kind == 'laplace' else AuxGaussIVA
+    model = cls(algorithm_spatial=spatial)
+    out = model(X, iteration=iters, demix_filter=W0)
+    want = {'output': out, 'demix_filter': model.demix_filter, 'loss': np.array(model.loss)}
+    o_out, st, o_loss = auxiva.run(X, iteration=iters, kind=kind, spatial=spatial, W=W0)
+    got = {'output': o_out, 'demix_filter': st['W'] if st['W'] is not None else st['W_final'],
+           'loss': np.array(o_loss)}
+    check(name, got, want, TOL if spatial not in ('IP2', 'pairwise') else 1e-7)
+    save(name, dict(model='AuxLaplaceIVA' if kind == 'laplace' else 'AuxGaussIVA',
+                    algorithm_spatial=spatial, iteration=iters), {'X': X, 'W0': W0}, want)
+
+
+# ------------------------------------------------------------------------------- FastMNMF
+
+def case_fastmnmf(name, M, N, F, T, K, iters):
+    X = synth.mix2(M, F, T, K=2, seed=3)
+    rng = np.random.default_rng(5)
+    W0 = rng.random((N, F, K)).astype(np.float32).astype(np.float64)
+    H0 = rng.random((N, K, T)).astype(np.float32).astype(np.float64)
+    model = FastMultichannelISNMF(n_basis=K, n_sources=N)
+    out = model(X, iteration=iters, basis=W0, activation=H0)
+    want = {'output': out, 'basis': model.basis, 'activation': model.activation,
+            'diagonalizer': model.diagonalizer, 'spatial_covariance': model.spatial_covariance,
+            'loss': np.array(model.loss)}
+    o_out, st, o_loss = fastmnmf.run(X, iteration=iters, n_basis=K, n_sources=N, W=W0, H=H0)
+    check(name, {'output': o_out, 'basis': st['W'], 'activation': st['H'], 'diagonalizer': st['Q'],
+                 'spatial_covariance': st['G'], 'loss': np.array(o_loss)}, want)
+    save(name, dict(model='FastMNMF', n_basis=K, n_sources=N, iteration=iters),
+         {'X': X, 'W0': W0, 'H0': H0}, want)
+
+
+# ------------------------------------------------------------------------------- NMF
+
+def case_nmf(name, kind, F, T, K, iters, domain=2, algorithm='mm', nu=1e3, seed=111):
+    Z = synth.spectrogram(F, T, seed=4)
+    if kind in ('euc', 'kl') and domain == 1:
+        Z = np.sqrt(Z).astype(np.float32).astype(np.float64)
+    cls = {'euc': EUCNMF, 'kl': KLNMF, 'is': ISNMF, 't': tNMF, 'cauchy': CauchyNMF}[kind]
+    if kind == 't':
+        model = cls(n_basis=K, nu=nu, domain=domain, algorithm=algorithm)
+    elif kind == 'cauchy':
+        model = cls(n_basis=K, domain=domain, algorithm=algorithm)
+    else:
+        model = cls(n_basis=K, domain=domain, algorithm=algorithm)
+    # NMFbase._reset always redraws (src/algorithm/nmf.py:42-43): seed the global RNG identically.
+    np.random.seed(seed)
+    Tr, Vr = model(Z, iteration=iters)
+    want = {'basis': Tr, 'activation': Vr, 'loss': np.array(model.loss)}
+    np.random.seed(seed)
+    To, Vo, lo = nmf.run(kind, Z, n_basis=K, iteration=iters, domain=domain, algorithm=algorithm, nu=nu)
+    check(name, {'basis': To, 'activation': Vo, 'loss': np.array(lo)}, want)
+    np.random.seed(seed)
+    T0 = np.random.rand(F, K)
+    V0 = np.random.rand(K, T)
+    save(name, dict(model=kind, n_basis=K, domain=domain, algorithm=algorithm, nu=nu, iteration=iters, seed=seed),
+         {'Z': Z, 'T0': T0, 'V0': V0}, want)
+
+
+# ------------------------------------------------------------------------------- primitives
+
+def case_primitives():
+    C, F, T = 3, 9, 20
+    X = synth.mix2(C, F, T, seed=6)
+    rng = np.random.default_rng(9)
+    # weighted covariance exactly as src/bss/ilrma.py:503-511
+    R = 10 ** rng.uniform(-6, 2, size=(C, F, T))
+    Xr = X.transpose(1, 2, 0)[..., np.newaxis]
+    XX = Xr @ Xr.transpose(0, 1, 3, 2).conj()
+    U = (XX / R[..., np.newaxis, np.newaxis]).mean(axis=2)
+    assert rel(core.weighted_covariance(X, R), U) < 1e-14
+    # projection back (2-D and 3-D reference)
+    W = synth.random_demix(C, F, seed=3)
+    Y = core.demix(X, W)
+    s2 = projection_back(Y, reference=X[0])
+    s3 = projection_back(Y, reference=X)
+    assert rel(core.projection_back_scale(Y, X[0]), s2) < 1e-14
+    assert rel(core.projection_back_scale(Y, X), s3) < 1e-14
+    # parallel_sort: integer gather, must be bit exact
+    v = rng.standard_normal((F, 2, 2)) + 1j * rng.standard_normal((F, 2, 2))
+    lam = rng.standard_normal((F, 2)) + 1j * rng.standard_normal((F, 2))
+    order = np.argsort(lam, axis=-1)[:, ::-1]
+    ps = parallel_sort(v.swapaxes(-2, -1), order=order, axis=-2)
+    assert np.array_equal(core.gather_by_order(v.swapaxes(-2, -1), order, axis=-2), ps)
+    # pair schedule (src/bss/ilrma.py:635-646)
+    sched = {}
+    for n_src in (2, 3, 4):
+        m = GaussILRMA(n_basis=2, algorithm_spatial='IP2')
+        m.n_sources = n_src
+        seq, pair = [], None
+        for _ in range(7):
+            m._select_update_pair()
+            pair = core.next_update_pair(pair, n_src)
+            assert tuple(m.update_pair) == tuple(pair)
+            seq.append(m.update_pair)
+        sched[str(n_src)] = np.array(seq)
+    save('primitives', dict(model='primitives'),
+         {'X': X, 'R': R, 'W': W, 'eigvec': v, 'eigval': lam},
+         {'U': U, 'scale2': s2, 'scale3': s3, 'order': order, 'sorted': ps,
+          'pairs2': sched['2'], 'pairs3': sched['3'], 'pairs4': sched['4']})
+
+
+def case_seeded_dropin():
+    """No injected state: both paths must consume np.random identically (src/bss/ilrma.py:97-104)."""
+    C, F, T, K = 2, 17, 30, 3
+    X = synth.mix2(C, F, T, seed=8)
+    np.random.seed(111)
+    model = GaussILRMA(n_basis=K)
+    out = model(X, iteration=3)
+    want = {'output': out, 'basis': model.basis, 'activation': model.activation,
+            'demix_filter': model.demix_filter, 'loss': np.array(model.loss)}
+    np.random.seed(111)
+    o_out, st, o_loss = ilrma.run(X, iteration=3, n_basis=K)
+    check('seeded', {'output': o_out, 'basis': st['T'], 'activation': st['V'], 'demix_filter': st['W'],
+                     'loss': np.array(o_loss)}, want)
+    save('ilrma_seeded_dropin', dict(model='GaussILRMA', n_basis=K, domain=2, partitioning=False,
+                                     normalize='power', algorithm_spatial='IP', iteration=3, seed=111),
+         {'X': X}, want)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    print("pinning oracle against /root/reference (numpy {}), tol {:g}".format(np.__version__, TOL))
+    case_primitives()
+    case_seeded_dropin()
+    case_ilrma('ilrma_ip_power_d2', 4, 33, 48, 2, 'IP', 'power', 2, 4)
+    case_ilrma('ilrma_ip_power_d1', 3, 17, 40, 3, 'IP', 'power', 1, 3)
+    case_ilrma('ilrma_ip_pb_d2', 2, 17, 40, 2, 'IP', 'projection-back', 2, 3)
+    case_ilrma('ilrma_iss_power_d2', 3, 17, 40, 2, 'ISS', 'power', 2, 3)
+    case_ilrma('ilrma_iss_pb_d1', 2, 17, 40, 2, 'ISS', 'projection-back', 1, 3)
+    case_ilrma('ilrma_ip2_power_d2', 3, 17, 40, 2, 'IP2', 'power', 2, 4)
+    case_ilrma('ilrma_ip2_power_c2', 2, 17, 40, 2, 'IP2', 'power', 2, 3)
+    case_ilrma('ilrma_ip_power_part', 3, 17, 40, 4, 'IP', 'power', 2, 3, partitioning=True)
+    case_tilrma('tilrma_nu5', 3, 17, 40, 2, 5.0, 3)
+    case_auxiva('auxiva_laplace_ip', 'laplace', 2, 33, 40, 'IP', 4)
+    case_auxiva('auxiva_laplace_ip_c4', 'laplace', 4, 17, 40, 'IP', 3)
+    case_auxiva('auxiva_gauss_ip', 'gauss', 3, 17, 40, 'IP', 3)
+    case_auxiva('auxiva_laplace_iss', 'laplace', 3, 17, 40, 'ISS', 3)
+    case_auxiva('auxiva_gauss_iss', 'gauss', 2, 17, 40, 'ISS', 3)
+    case_auxiva('auxiva_laplace_ip2', 'laplace', 3, 17, 40, 'IP2', 4)
+    case_fastmnmf('fastmnmf_m3n3', 3, 3, 17, 40, 2, 3)
+    case_fastmnmf('fastmnmf_m4n2', 4, 2, 9, 32, 3, 2)
+    case_nmf('nmf_euc_d2', 'euc', 33, 24, 4, 5, domain=2)
+    case_nmf('nmf_euc_d1', 'euc', 33, 24, 4, 5, domain=1)
+    case_nmf('nmf_kl_d2', 'kl', 33, 24, 4, 5, domain=2)
+    case_nmf('nmf_kl_d1', 'kl', 33, 24, 3, 5, domain=1)
+    case_nmf('nmf_is_mm_d2', 'is', 33, 24, 4, 5, domain=2)
+    case_nmf('nmf_is_mm_d1', 'is', 33, 24, 4, 5, domain=1)
+    case_nmf('nmf_is_me', 'is', 33, 24, 4, 5, domain=2, algorithm='me')
+    case_nmf('nmf_t', 't', 33, 24, 4, 5, nu=50.0)
+    for alg in ('naive-multipricative', 'mm', 'me', 'mm_fast'):
+        case_nmf('nmf_cauchy_' + alg.replace('-', '_'), 'cauchy', 33, 24, 4, 5, algorithm=alg)
+    print("all oracle functions pinned against the reference.")
+
+
+if __name__ == '__main__':
+    main()
