@@ -1,0 +1,285 @@
+"""ctypes binding of libbssgpu.so (the C ABI declared in include/bssgpu.h).
+
+There is no CPU path: if the shared library is missing, or the machine has no B200-class GPU, the
+first use raises.  Nothing here imports `oracle/`.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbssgpu.so')
+
+# enum bss_status
+OK, EINVAL, ECUDA, ESINGULAR, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+# enum bss_method
+GAUSS_ILRMA, T_ILRMA, AUX_LAPLACE_IVA, AUX_GAUSS_IVA, FAST_MNMF = 0, 1, 2, 3, 4
+NMF_EUC, NMF_KL, NMF_IS, NMF_T, NMF_CAUCHY = 10, 11, 12, 13, 14
+# enum bss_spatial / bss_normalize / bss_nmf_algorithm
+SPATIAL_IP, SPATIAL_ISS, SPATIAL_IP2 = 0, 1, 2
+NORMALIZE_NONE, NORMALIZE_POWER, NORMALIZE_PROJECTION_BACK = 0, 1, 2
+ALG_MM, ALG_ME, ALG_NAIVE, ALG_MM_FAST = 0, 1, 2, 3
+# enum bss_dtype
+F32, F64, C64, C128, I32 = 0, 1, 2, 3, 4
+# enum bss_state
+(STATE_DEMIX_FILTER, STATE_ESTIMATION, STATE_BASIS, STATE_ACTIVATION, STATE_LATENT, STATE_DIAGONALIZER,
+ STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE) = range(10)
+
+_DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64,
+           np.dtype(np.complex128): C128, np.dtype(np.int32): I32}
+
+
+class Config(ctypes.Structure):
+    _fields_ = [
+        ('method', ctypes.c_int32), ('spatial', ctypes.c_int32), ('normalize', ctypes.c_int32),
+        ('partitioning', ctypes.c_int32), ('algorithm', ctypes.c_int32), ('n_batch', ctypes.c_int32),
+        ('n_channels', ctypes.c_int32), ('n_sources', ctypes.c_int32), ('n_bins', ctypes.c_int32),
+        ('n_frames', ctypes.c_int32), ('n_basis', ctypes.c_int32), ('reference_id', ctypes.c_int32),
+        ('device', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('domain', ctypes.c_double), ('nu', ctypes.c_double), ('eps', ctypes.c_double), ('threshold', ctypes.c_double),
+    ]
+
+
+# every symbol include/bssgpu.h declares: name -> (restype, argtypes)
+_vp, _i, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+SIGNATURES = {
+    'bss_create': (_i, [ctypes.POINTER(Config), ctypes.POINTER(_vp)]),
+    'bss_destroy': (None, [_vp]),
+    'bss_last_error': (ctypes.c_char_p, [_vp]),
+    'bss_set_stream': (_i, [_vp, _vp]),
+    'bss_synchronize': (_i, [_vp]),
+    'bss_set_input': (_i, [_vp, _vp, _i]),
+    'bss_set_state': (_i, [_vp, _i, _vp, _i]),
+    'bss_get_state': (_i, [_vp, _i, _vp, _i]),
+    'bss_reset_spatial': (_i, [_vp]),
+    'bss_set_update_pair': (_i, [_vp, _i, _i]),
+    'bss_update_once': (_i, [_vp]),
+    'bss_run': (_i, [_vp, _i]),
+    'bss_loss': (_i, [_vp, ctypes.POINTER(_d)]),
+    'bss_separate': (_i, [_vp, _vp, _i, _i]),
+    'bss_separate_device': (_i, [_vp, _vp, _i]),
+    'bss_compute_demix_filter': (_i, [_vp]),
+    'bss_weighted_covariance': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'bss_ip_update': (_i, [_i, _i, _i, _vp, _vp, _vp, _d, _i, _d]),
+    'bss_projection_back_scale': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    'bss_demix': (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+    'bss_timer_begin': (_i, [_vp]),
+    'bss_timer_end': (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    'bss_time_covariance': (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
+    'bss_launch_count': (ctypes.c_int64, [_vp]),
+    'bss_device_buffer': (_i, [_vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t)]),
+    'bss_version': (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load libbssgpu.so and bind every entry point (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libbssgpu.so is not built ({}). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C audio_source_separation_b200/csrc`. There is no CPU implementation.".format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _raise(code, message):
+    if code == ESINGULAR:
+        raise np.linalg.LinAlgError(message or "Singular matrix")
+    if code == EINVAL:
+        raise ValueError(message)
+    if code == EUNSUPPORTED:
+        raise NotImplementedError(message)
+    if code == ENOMEM:
+        raise MemoryError(message)
+    raise RuntimeError("libbssgpu error {}: {}".format(code, message))
+
+
+def check_static(code, what):
+    if code != OK:
+        _raise(code, "{} failed".format(what) + (": " + load().bss_last_error(None).decode() if code != ESINGULAR else ""))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def as_host(a, dtype):
+    """C-contiguous array of exactly `dtype` (no copy when it already is one)."""
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Handle:
+    """Owns one bss_handle: a batch of B mixtures resident on one GPU."""
+
+    def __init__(self, **cfg):
+        lib = load()
+        c = Config()
+        defaults = dict(method=GAUSS_ILRMA, spatial=SPATIAL_IP, normalize=NORMALIZE_POWER, partitioning=0, algorithm=ALG_MM,
+                        n_batch=1, n_channels=0, n_sources=0, n_bins=0, n_frames=0, n_basis=1, reference_id=0, device=0,
+                        reserved=0, domain=2.0, nu=1.0, eps=1e-12, threshold=1e12)
+        defaults.update(cfg)
+        for k, v in defaults.items():
+            setattr(c, k, v)
+        self.cfg = defaults
+        self._h = ctypes.c_void_p()
+        self._lib = lib
+        code = lib.bss_create(ctypes.byref(c), ctypes.byref(self._h))
+        if code != OK:
+            self._h = None
+            _raise(code, lib.bss_last_error(None).decode())
+
+    # shapes -------------------------------------------------------------------------------------
+    @property
+    def B(self):
+        return self.cfg['n_batch']
+
+    def _check(self, code):
+        if code != OK:
+            _raise(code, self._lib.bss_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.bss_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # data movement ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.bss_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.bss_synchronize(self._h))
+
+    def set_input(self, x):
+        if x.dtype != np.complex64:
+            x = as_host(x, np.complex128)
+        else:
+            x = as_host(x, np.complex64)
+        self._check(self._lib.bss_set_input(self._h, _ptr(x), _DTYPES[x.dtype]))
+
+    def set_input_ptr(self, ptr, dtype):
+        """Input already sitting in (pinned) host memory at address `ptr`."""
+        self._check(self._lib.bss_set_input(self._h, ctypes.c_void_p(ptr), dtype))
+
+    def set_state(self, which, a, dtype):
+        a = as_host(a, dtype)
+        self._check(self._lib.bss_set_state(self._h, which, _ptr(a), _DTYPES[a.dtype]))
+
+    def get_state(self, which, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self._lib.bss_get_state(self._h, which, _ptr(out), _DTYPES[out.dtype]))
+        return out
+
+    def reset_spatial(self):
+        self._check(self._lib.bss_reset_spatial(self._h))
+
+    # update loop --------------------------------------------------------------------------------
+    def set_update_pair(self, m, n):
+        self._check(self._lib.bss_set_update_pair(self._h, int(m), int(n)))
+
+    def update_once(self):
+        self._check(self._lib.bss_update_once(self._h))
+
+    def run(self, n_iter):
+        self._check(self._lib.bss_run(self._h, int(n_iter)))
+
+    def loss(self):
+        out = (ctypes.c_double * self.B)()
+        self._check(self._lib.bss_loss(self._h, out))
+        return np.array(out[:], dtype=np.float64)
+
+    def separate(self, shape, dtype=np.complex128, projection_back=True):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self._lib.bss_separate(self._h, _ptr(out), _DTYPES[out.dtype], 1 if projection_back else 0))
+        return out
+
+    def separate_into(self, ptr, dtype, projection_back=True):
+        self._check(self._lib.bss_separate(self._h, ctypes.c_void_p(ptr), dtype, 1 if projection_back else 0))
+
+    def separate_device(self, device_ptr, projection_back=True):
+        self._check(self._lib.bss_separate_device(self._h, ctypes.c_void_p(device_ptr), 1 if projection_back else 0))
+
+    def compute_demix_filter(self):
+        self._check(self._lib.bss_compute_demix_filter(self._h))
+
+    # measurement --------------------------------------------------------------------------------
+    def timer_begin(self):
+        self._check(self._lib.bss_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = ctypes.c_float()
+        self._check(self._lib.bss_timer_end(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def time_covariance(self, repeat):
+        ms = ctypes.c_float()
+        self._check(self._lib.bss_time_covariance(self._h, int(repeat), ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self._lib.bss_launch_count(self._h))
+
+
+# stateless primitives ---------------------------------------------------------------------------
+
+def weighted_covariance(x, r, device=0):
+    """U[n,f] = mean_t x x^H / r[n,f,t]; x (C,F,T), r broadcastable to (N,F,T) -> (N,F,C,C) complex128."""
+    lib = load()
+    x = as_host(x, np.complex128)
+    C, F, T = x.shape
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64), (C, F, T)))
+    u = np.empty((C, F, C, C), dtype=np.complex128)
+    code = lib.bss_weighted_covariance(device, C, C, F, T, _ptr(x), _ptr(r), _ptr(u))
+    check_static(code, 'bss_weighted_covariance')
+    return u
+
+
+def ip_update(w, u, threshold=1e12, floor_den=False, eps=1e-12, device=0):
+    """Gauss-Seidel IP sweep; returns (W_new (F,N,C), gate (N,F) bool)."""
+    lib = load()
+    w = np.array(w, dtype=np.complex128, order='C', copy=True)
+    u = as_host(u, np.complex128)
+    F, N, C = w.shape
+    gate = np.empty((N, F), dtype=np.int32)
+    code = lib.bss_ip_update(device, C, F, _ptr(w), _ptr(u), _ptr(gate), float(threshold), 1 if floor_den else 0, float(eps))
+    check_static(code, 'bss_ip_update')
+    return w, gate.astype(bool)
+
+
+def projection_back_scale(x, w, reference_id=0, device=0):
+    lib = load()
+    x = as_host(x, np.complex128)
+    w = as_host(w, np.complex128)
+    C, F, T = x.shape
+    scale = np.empty((C, F), dtype=np.complex128)
+    code = lib.bss_projection_back_scale(device, C, F, T, _ptr(x), _ptr(w), int(reference_id), _ptr(scale))
+    check_static(code, 'bss_projection_back_scale')
+    return scale
+
+
+def demix(x, w, device=0):
+    """Y[n,f,t] = sum_c W[f,n,c] X[c,f,t] on the GPU (complex64 arithmetic), returned as complex128."""
+    lib = load()
+    x = as_host(x, np.complex128)
+    w = as_host(w, np.complex128)
+    C, F, T = x.shape
+    y = np.empty((w.shape[1], F, T), dtype=np.complex128)
+    code = lib.bss_demix(device, C, F, T, 0, _ptr(x), _ptr(w), _ptr(y))
+    check_static(code, 'bss_demix')
+    return y

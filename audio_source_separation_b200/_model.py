@@ -1,0 +1,161 @@
+"""Host-side plumbing shared by the drop-in model classes.
+
+The reference models (src/bss/ilrma.py, src/bss/iva.py, src/bss/mnmf.py) keep all state as public
+NumPy attributes that callbacks and users read and assign between iterations.  Here the state lives on
+the GPU; `DeviceModel` keeps that attribute protocol working:
+
+  * reading `model.basis` (etc.) fetches the tensor from the device once and caches it until the next
+    device-side update;
+  * assigning `model.basis = a` (or mutating a fetched array in place) is uploaded before the next
+    device-side operation;
+  * `hasattr(model, 'basis')` is False until the state exists, exactly as the reference's `_reset`
+    relies on (src/bss/ilrma.py:67-104).
+"""
+import numpy as np
+
+from . import _lib
+
+
+class DeviceModel:
+    # name -> state id; filled by subclasses
+    _STATE_IDS = {}
+    # states whose fetched copies are small enough to snapshot for in-place mutation detection
+    _SNAPSHOT = ('demix_filter', 'basis', 'activation', 'latent', 'diagonalizer', 'spatial_covariance')
+
+    def __init__(self):
+        d = self.__dict__
+        d['_host'] = {}        # name -> ndarray or None (valid host mirrors)
+        d['_dirty'] = set()    # names assigned on the host since the last upload
+        d['_snap'] = {}        # name -> copy taken when a fetched array was handed out
+        d['_on_device'] = set()
+        d['_handle'] = None
+        d['_handle_key'] = None
+        d['_input_token'] = None
+
+    # -- attribute protocol ----------------------------------------------------------------------
+    def __setattr__(self, name, value):
+        if name in self._STATE_IDS:
+            self._host[name] = value
+            self._snap.pop(name, None)
+            if value is None:
+                self._dirty.discard(name)
+            else:
+                self._dirty.add(name)
+        else:
+            object.__setattr__(self, name, value)
+
+    def __getattr__(self, name):
+        # only called when normal lookup fails
+        ids = type(self)._STATE_IDS
+        if name in ids:
+            d = self.__dict__
+            host = d.get('_host', {})
+            if name in host:
+                return host[name]
+            if name in d.get('_on_device', ()) and d.get('_handle') is not None:
+                arr = self._fetch(name)
+                host[name] = arr
+                if name in self._SNAPSHOT:
+                    d['_snap'][name] = arr.copy()
+                return arr
+        raise AttributeError("'{}' object has no attribute '{}'".format(type(self).__name__, name))
+
+    def __delattr__(self, name):
+        if name in self._STATE_IDS:
+            self._host.pop(name, None)
+            self._dirty.discard(name)
+            self._snap.pop(name, None)
+            self._on_device.discard(name)
+        else:
+            object.__delattr__(self, name)
+
+    # -- to be provided by subclasses ----------------------------------------------------------------
+    def _state_shape(self, name):
+        raise NotImplementedError
+
+    def _state_dtype(self, name):
+        return np.complex128 if name in ('demix_filter', 'estimation', 'diagonalizer') else np.float64
+
+    # -- device synchronisation ----------------------------------------------------------------------
+    def _fetch(self, name):
+        return self._handle.get_state(self._STATE_IDS[name], self._state_shape(name), self._state_dtype(name))
+
+    def _upload(self, name, value):
+        shape = self._state_shape(name)
+        value = np.asarray(value)
+        if tuple(value.shape) != tuple(shape):
+            raise ValueError("{} has shape {}, expected {}".format(name, tuple(value.shape), tuple(shape)))
+        self._handle.set_state(self._STATE_IDS[name], value, self._state_dtype(name))
+        self._on_device.add(name)
+
+    def _push(self):
+        """Upload everything the host changed since the last device operation."""
+        for name in list(self._dirty):
+            value = self._host.get(name)
+            if value is not None and name != 'estimation':
+                self._upload(name, value)
+        self._dirty.clear()
+        for name, snap in list(self._snap.items()):
+            cur = self._host.get(name)
+            if cur is not None and not np.array_equal(cur, snap):
+                self._upload(name, cur)
+                self._snap[name] = np.array(cur, copy=True)
+
+    def _device_changed(self, *names):
+        """The device copies of `names` (default: all) are newer than any host mirror."""
+        names = names or tuple(self._on_device)
+        for name in names:
+            self._host.pop(name, None)
+            self._snap.pop(name, None)
+
+    def _open_handle(self, key, **cfg):
+        """(Re)create the device handle when the problem shape or configuration changed."""
+        if self._handle is not None and self._handle_key == key:
+            return False
+        if self._handle is not None:
+            # keep what the host can still see of the old state
+            for name in list(self._on_device):
+                if name not in self._host:
+                    try:
+                        self._host[name] = self._fetch(name)
+                        self._dirty.add(name)
+                    except Exception:
+                        pass
+            self._handle.close()
+        self.__dict__['_handle'] = _lib.Handle(**cfg)
+        self.__dict__['_handle_key'] = key
+        self.__dict__['_on_device'] = set()
+        self.__dict__['_input_token'] = None
+        for name, value in self._host.items():
+            if value is not None:
+                self._dirty.add(name)
+        self._snap.clear()
+        return True
+
+    def _send_input(self, X):
+        token = (id(X), X.shape, X.dtype.str)
+        if self._input_token != token:
+            self._handle.set_input(X)
+            self.__dict__['_input_token'] = token
+            return True
+        return False
+
+
+def parse_spatial(name):
+    if name in ('IP', 'IP1'):
+        return _lib.SPATIAL_IP
+    if name == 'ISS':
+        return _lib.SPATIAL_ISS
+    if name in ('pairwise', 'IP2'):
+        return _lib.SPATIAL_IP2
+    raise NotImplementedError("Not support {}-based spatial update.".format(name))
+
+
+def parse_normalize(value):
+    if not value:
+        return _lib.NORMALIZE_NONE
+    if value == 'power':
+        return _lib.NORMALIZE_POWER
+    if value == 'projection-back':
+        return _lib.NORMALIZE_PROJECTION_BACK
+    raise ValueError("Not support normalization based on {}. Choose 'power' or 'projection-back'".format(value))

@@ -1,0 +1,111 @@
+"""Batches of independent mixtures (our extension: the reference has no batch axis, one model == one mixture).
+
+`BatchedGaussILRMA` runs B Gauss-ILRMA problems of identical shape side by side on one GPU: every kernel
+takes the mixture index as an extra grid dimension, nothing is shared between mixtures, and the results
+are identical to B separate `GaussILRMA` runs.  `shard_range` / `gather_outputs` split a batch over the
+ranks of a torch.distributed job (one process per GPU); the only communication is the final all-gather of
+the separated outputs over NCCL.
+"""
+import numpy as np
+
+from . import _lib
+from ._model import parse_spatial, parse_normalize
+
+EPS = 1e-12
+THRESHOLD = 1e+12
+
+
+class BatchedGaussILRMA:
+    def __init__(self, n_basis=10, domain=2, normalize='power', algorithm_spatial='IP', reference_id=0, eps=EPS,
+                 threshold=THRESHOLD, device=0):
+        assert 1 <= domain <= 2, "1 <= `domain` <= 2 is not satisfied."
+        self.n_basis = n_basis
+        self.domain = domain
+        self.normalize = normalize
+        self.algorithm_spatial = algorithm_spatial
+        self.reference_id = reference_id
+        self.eps = eps
+        self.threshold = threshold
+        self.device = device
+        self.handle = None
+        self._key = None
+
+    def open(self, B, C, F, T):
+        key = (B, C, F, T)
+        if self.handle is not None and self._key == key:
+            return self.handle
+        if self.handle is not None:
+            self.handle.close()
+        self.handle = _lib.Handle(method=_lib.GAUSS_ILRMA, spatial=parse_spatial(self.algorithm_spatial),
+                                  normalize=parse_normalize(self.normalize), n_batch=B, n_channels=C, n_sources=C, n_bins=F,
+                                  n_frames=T, n_basis=self.n_basis, reference_id=self.reference_id, device=self.device,
+                                  domain=float(self.domain), eps=float(self.eps), threshold=float(self.threshold))
+        self._key = key
+        self.shape = key
+        return self.handle
+
+    def reset(self, X, demix_filter=None, basis=None, activation=None):
+        """Upload a batch (B,C,F,T) and its initial state; missing state is drawn like the reference's `_reset`
+        (np.random.rand: basis (B,N,F,K) first, then activation (B,N,K,T))."""
+        B, C, F, T = X.shape
+        h = self.open(B, C, F, T)
+        h.set_input(X)
+        K = self.n_basis
+        if demix_filter is None:
+            h.reset_spatial()
+        else:
+            h.set_state(_lib.STATE_DEMIX_FILTER, demix_filter, np.complex128)
+        if basis is None:
+            basis = np.random.rand(B, C, F, K)
+        if activation is None:
+            activation = np.random.rand(B, C, K, T)
+        h.set_state(_lib.STATE_BASIS, basis, np.float64)
+        h.set_state(_lib.STATE_ACTIVATION, activation, np.float64)
+        return h
+
+    def __call__(self, X, iteration=100, dtype=np.complex128, **presets):
+        """X (B,C,F,T) -> projection-backed estimates (B,N,F,T)."""
+        h = self.reset(X, **presets)
+        h.run(iteration)
+        B, C, F, T = X.shape
+        return h.separate((B, C, F, T), dtype, projection_back=True)
+
+    def update_once(self):
+        self.handle.update_once()
+
+    def compute_negative_loglikelihood(self):
+        return self.handle.loss()
+
+    @property
+    def demix_filter(self):
+        B, C, F, T = self.shape
+        return self.handle.get_state(_lib.STATE_DEMIX_FILTER, (B, F, C, C), np.complex128)
+
+    @property
+    def basis(self):
+        B, C, F, T = self.shape
+        return self.handle.get_state(_lib.STATE_BASIS, (B, C, F, self.n_basis), np.float64)
+
+    @property
+    def activation(self):
+        B, C, F, T = self.shape
+        return self.handle.get_state(_lib.STATE_ACTIVATION, (B, C, self.n_basis, T), np.float64)
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous shard [lo, hi) of rank `rank` (earlier ranks take the remainder)."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_outputs(local, world_size, group=None):
+    """All-gather per-rank outputs (torch tensors of equal shape, complex64 viewed as float32 pairs) along the
+    batch axis.  The single collective of the sharded path; runs on NCCL for CUDA tensors, gloo for CPU ones."""
+    import torch
+    import torch.distributed as dist
+    if world_size == 1:
+        return local
+    parts = [torch.empty_like(local) for _ in range(world_size)]
+    dist.all_gather(parts, local, group=group)
+    return torch.cat(parts, dim=0)

@@ -1,0 +1,370 @@
+// C ABI of libbssgpu.so (see include/bssgpu.h): handle life cycle, host <-> device state
+// movement and the orchestration of one update_once per method.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "handle.h"
+#include "methods.h"
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+bool is_nmf(int m) { return m >= BSS_NMF_EUC && m <= BSS_NMF_CAUCHY; }
+bool is_ilrma(int m) { return m == BSS_GAUSS_ILRMA || m == BSS_T_ILRMA; }
+bool is_iva(int m) { return m == BSS_AUX_LAPLACE_IVA || m == BSS_AUX_GAUSS_IVA; }
+
+template <typename T>
+int dev_alloc(bss_handle* h, T** p, size_t n) {
+    if (n == 0) n = 1;
+    BSS_CUDA(h, cudaMalloc((void**)p, n * sizeof(T)));
+    BSS_CUDA(h, cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream));
+    return BSS_OK;
+}
+
+int validate(const bss_config* c, std::string* why) {
+    auto bad = [&](const char* m) {
+        *why = m;
+        return BSS_EINVAL;
+    };
+    if (c->n_batch < 1) return bad("n_batch must be >= 1");
+    if (c->n_bins < 1 || c->n_frames < 1) return bad("n_bins and n_frames must be >= 1");
+    if (c->n_basis < 1 || c->n_basis > 64) return bad("n_basis must be between 1 and 64");
+    if (is_nmf(c->method)) {
+        if (!(c->domain >= 1.0 && c->domain <= 2.0)) return bad("1 <= `domain` <= 2 is not satisfied.");
+        return BSS_OK;
+    }
+    if (c->n_channels < 2 || c->n_channels > 8) return bad("n_channels must be between 2 and 8");
+    if (c->method == BSS_FAST_MNMF) {
+        if (c->n_sources < 1 || c->n_sources > 8) return bad("n_sources must be between 1 and 8");
+    } else {
+        if (c->n_sources != c->n_channels) return bad("determined methods need n_sources == n_channels");
+    }
+    if (c->method == BSS_GAUSS_ILRMA && !(c->domain >= 1.0 && c->domain <= 2.0))
+        return bad("1 <= `domain` <= 2 is not satisfied.");
+    if (c->reference_id < 0 || c->reference_id >= c->n_channels) return bad("reference_id out of range");
+    if (c->spatial < BSS_SPATIAL_IP || c->spatial > BSS_SPATIAL_IP2) return bad("unknown algorithm_spatial");
+    if (c->spatial == BSS_SPATIAL_IP2 && c->n_sources < 2) return bad("IP2 needs at least two sources");
+    switch (c->method) {
+        case BSS_GAUSS_ILRMA:
+        case BSS_T_ILRMA:
+        case BSS_AUX_LAPLACE_IVA:
+        case BSS_AUX_GAUSS_IVA:
+        case BSS_FAST_MNMF: break;
+        default: return bad("unknown method");
+    }
+    return BSS_OK;
+}
+
+// surface exactly singular bins (the reference raises LinAlgError there); requires a sync
+int check_flags(bss_handle* h) {
+    int32_t flag = 0;
+    BSS_CUDA(h, cudaMemcpyAsync(&flag, h->flags, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag != 0) {
+        cudaMemsetAsync(h->flags, 0, sizeof(int32_t), h->stream);
+        return bss_fail(h, BSS_ESINGULAR, "Singular matrix");
+    }
+    return BSS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bss_version(void) { return "bssgpu 0.1 (sm_100a)"; }
+
+const char* bss_last_error(const bss_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t bss_launch_count(const bss_handle* h) { return h ? h->launches : 0; }
+
+int bss_create(const bss_config* cfg, bss_handle** out) {
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return BSS_EINVAL;
+    }
+    *out = nullptr;
+    std::string why;
+    if (validate(cfg, &why) != BSS_OK) {
+        g_create_error = why;
+        return BSS_EINVAL;
+    }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (libbssgpu has no CPU path)";
+        return BSS_ECUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev) {
+        g_create_error = "device ordinal out of range";
+        return BSS_EINVAL;
+    }
+    bss_handle* h = new (std::nothrow) bss_handle();
+    if (!h) {
+        g_create_error = "out of host memory";
+        return BSS_ENOMEM;
+    }
+    h->cfg = *cfg;
+    h->B = cfg->n_batch;
+    h->C = cfg->n_channels;
+    h->N = cfg->n_sources;
+    h->F = cfg->n_bins;
+    h->T = cfg->n_frames;
+    h->Tp = round_up(cfg->n_frames, 2);
+    h->K = cfg->n_basis;
+    auto fail = [&](int rc) {
+        g_create_error = h->err;
+        bss_destroy(h);
+        return rc;
+    };
+#define CREATE_CUDA(call)                                                   \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) {                                           \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);   \
+            return fail(BSS_ECUDA);                                         \
+        }                                                                   \
+    } while (0)
+    CREATE_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) {
+        h->err = "libbssgpu is built for sm_100a (B200) only";
+        return fail(BSS_ECUDA);
+    }
+    h->n_sm = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CREATE_CUDA(cudaEventCreate(&h->ev0));
+    CREATE_CUDA(cudaEventCreate(&h->ev1));
+    int rc = dev_alloc(h, &h->flags, 4);
+    if (rc == BSS_OK) rc = is_nmf(cfg->method) ? nmf_allocate(h) : (cfg->method == BSS_FAST_MNMF ? mnmf_allocate(h) : bss_allocate(h));
+    if (rc != BSS_OK) return fail(rc);
+    CREATE_CUDA(cudaStreamSynchronize(h->stream));
+#undef CREATE_CUDA
+    *out = h;
+    return BSS_OK;
+}
+
+void bss_destroy(bss_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* bufs[] = {h->X,   h->Y,    h->W,     h->Wf,    h->basis, h->basis2, h->act,     h->latent, h->U,      h->Cx,
+                    h->gate, h->flags, h->pw,   h->scale, h->wfr,   h->wraw,   h->order,   h->logdet, h->aux,    h->G2,
+                    h->part, h->iw,   h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2};
+    for (void* p : bufs)
+        if (p) cudaFree(p);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int bss_set_stream(bss_handle* h, void* cuda_stream) {
+    if (!h) return BSS_EINVAL;
+    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return BSS_OK;
+}
+
+int bss_synchronize(bss_handle* h) {
+    if (!h) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    return check_flags(h);
+}
+
+int bss_timer_begin(bss_handle* h) {
+    if (!h) return BSS_EINVAL;
+    BSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    return BSS_OK;
+}
+
+int bss_timer_end(bss_handle* h, float* elapsed_ms) {
+    if (!h || !elapsed_ms) return BSS_EINVAL;
+    BSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    BSS_CUDA(h, cudaEventSynchronize(h->ev1));
+    BSS_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    return BSS_OK;
+}
+
+int bss_set_input(bss_handle* h, const void* x, int dtype) {
+    if (!h || !x) return BSS_EINVAL;
+    if (is_nmf(h->cfg.method)) return bss_fail(h, BSS_EINVAL, "NMF takes its target through bss_set_state");
+    if (dtype != BSS_C64 && dtype != BSS_C128) return bss_fail(h, BSS_EINVAL, "input must be complex64 or complex128");
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t elems = (size_t)h->B * h->C * h->F * h->T;
+    const size_t bytes = elems * (dtype == BSS_C128 ? 16 : 8);
+    BSS_TRY(ensure_staging(h, bytes));
+    BSS_CUDA(h, cudaMemcpyAsync(h->staging, x, bytes, cudaMemcpyHostToDevice, h->stream));
+    BSS_TRY(launch_import_x(h, h->staging, dtype, h->X, h->B, h->C, h->F, h->T, h->Tp));
+    // plain covariance mean_t x x^H (algebraic power normalisation / projection back)
+    CovArgs ca{};
+    ca.X = h->X;
+    ca.U = h->Cx;
+    ca.B = h->B;
+    ca.F = h->F;
+    ca.C = h->C;
+    ca.NW = 1;
+    ca.T = h->T;
+    ca.Tp = h->Tp;
+    ca.wmode = WM_UNIT;
+    ca.n_sel = 1;
+    ca.wsel[0] = 0;
+    BSS_TRY(launch_covariance(h, ca));
+    h->has_input = true;
+    h->y_valid = false;
+    // the caller's buffer may be reused as soon as we return
+    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BSS_OK;
+}
+
+int bss_reset_spatial(bss_handle* h) {
+    if (!h) return BSS_EINVAL;
+    if (is_nmf(h->cfg.method)) return BSS_OK;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.method == BSS_FAST_MNMF) return mnmf_reset(h);
+    return bss_reset_filter(h);
+}
+
+int bss_set_update_pair(bss_handle* h, int m, int n) {
+    if (!h) return BSS_EINVAL;
+    if (m < 0 || n < 0 || m >= h->N || n >= h->N || m == n) return bss_fail(h, BSS_EINVAL, "invalid update pair");
+    h->pair_m = m;
+    h->pair_n = n;
+    return BSS_OK;
+}
+
+int bss_update_once(bss_handle* h) {
+    if (!h) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (is_nmf(h->cfg.method)) return nmf_update_once(h);
+    if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    switch (h->cfg.method) {
+        case BSS_GAUSS_ILRMA: return ilrma_update_once(h);
+        case BSS_T_ILRMA: return tilrma_update_once(h);
+        case BSS_AUX_LAPLACE_IVA:
+        case BSS_AUX_GAUSS_IVA: return auxiva_update_once(h);
+        case BSS_FAST_MNMF: return mnmf_update_once(h);
+    }
+    return bss_fail(h, BSS_EINVAL, "unknown method");
+}
+
+int bss_run(bss_handle* h, int n_iter) {
+    if (!h || n_iter < 0) return BSS_EINVAL;
+    for (int i = 0; i < n_iter; ++i) {
+        if (!is_nmf(h->cfg.method) && h->cfg.spatial == BSS_SPATIAL_IP2 && h->cfg.method != BSS_FAST_MNMF) {
+            // src/bss/ilrma.py:635-646: (0,1) first, then +1 modulo N
+            if (h->pair_m < 0) {
+                h->pair_m = 0;
+                h->pair_n = 1;
+            } else {
+                h->pair_m = (h->pair_m + 1) % h->N;
+                h->pair_n = (h->pair_n + 1) % h->N;
+            }
+        }
+        BSS_TRY(bss_update_once(h));
+    }
+    return BSS_OK;
+}
+
+int bss_loss(bss_handle* h, double* loss) {
+    if (!h || !loss) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc;
+    if (is_nmf(h->cfg.method))
+        rc = nmf_loss(h);
+    else {
+        if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+        rc = h->cfg.method == BSS_FAST_MNMF ? mnmf_loss(h) : bss_loss_device(h);
+    }
+    if (rc != BSS_OK) return rc;
+    // results sit at lossbuf[B*F .. B*F+B)
+    BSS_CUDA(h, cudaMemcpyAsync(loss, h->lossbuf + (size_t)h->B * h->F, sizeof(double) * h->B, cudaMemcpyDeviceToHost,
+                                h->stream));
+    return check_flags(h);
+}
+
+int bss_separate_device(bss_handle* h, void* y_device, int apply_projection_back) {
+    if (!h || !y_device) return BSS_EINVAL;
+    if (is_nmf(h->cfg.method)) return bss_fail(h, BSS_EINVAL, "NMF has no separate()");
+    if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.method == BSS_FAST_MNMF) return mnmf_separate(h, (cf*)y_device);
+    return bss_separate_to(h, (cf*)y_device, apply_projection_back);
+}
+
+int bss_separate(bss_handle* h, void* y, int dtype, int apply_projection_back) {
+    if (!h || !y) return BSS_EINVAL;
+    if (dtype != BSS_C64 && dtype != BSS_C128) return bss_fail(h, BSS_EINVAL, "output must be complex64 or complex128");
+    const size_t elems = (size_t)h->B * h->N * h->F * h->T;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    BSS_TRY(ensure_staging(h, elems * 8));
+    BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
+    if (dtype == BSS_C64) {
+        BSS_CUDA(h, cudaMemcpyAsync(y, h->staging, elems * 8, cudaMemcpyDeviceToHost, h->stream));
+        return check_flags(h);
+    }
+    BSS_TRY(ensure_pinned(h, elems * 8));
+    BSS_CUDA(h, cudaMemcpyAsync(h->pinned, h->staging, elems * 8, cudaMemcpyDeviceToHost, h->stream));
+    BSS_TRY(check_flags(h));
+    const float* s = (const float*)h->pinned;
+    double* d = (double*)y;
+    for (size_t i = 0; i < elems * 2; ++i) d[i] = (double)s[i];
+    return BSS_OK;
+}
+
+int bss_compute_demix_filter(bss_handle* h) {
+    if (!h) return BSS_EINVAL;
+    if (is_nmf(h->cfg.method) || h->cfg.method == BSS_FAST_MNMF) return bss_fail(h, BSS_EINVAL, "no demixing filter");
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    return bss_filter_from_estimates(h);
+}
+
+int bss_device_buffer(bss_handle* h, int which, void** dptr, size_t* bytes) {
+    if (!h || !dptr) return BSS_EINVAL;
+    size_t n = 0;
+    void* p = nullptr;
+    switch (which) {
+        case BSS_STATE_DEMIX_FILTER:
+        case BSS_STATE_DIAGONALIZER:
+            p = h->W;
+            n = (size_t)h->B * h->F * h->C * h->C * 16;
+            break;
+        case BSS_STATE_ESTIMATION:
+            p = h->Y;
+            n = (size_t)h->B * h->F * h->N * h->Tp * 8;
+            break;
+        case BSS_STATE_BASIS: p = h->basis; break;
+        case BSS_STATE_ACTIVATION: p = h->act; break;
+        case BSS_STATE_COVARIANCE:
+            p = h->U;
+            n = (size_t)h->B * h->C * h->F * h->C * h->C * 8;
+            break;
+        default: return bss_fail(h, BSS_EINVAL, "no such device buffer");
+    }
+    *dptr = p;
+    if (bytes) *bytes = n;
+    return BSS_OK;
+}
+
+int bss_time_covariance(bss_handle* h, int repeat, float* mean_ms) {
+    if (!h || !mean_ms || repeat < 1) return BSS_EINVAL;
+    if (is_nmf(h->cfg.method) || !h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    BSS_TRY(bss_covariance_only(h));   // warm-up
+    BSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < repeat; ++i) BSS_TRY(bss_covariance_only(h));
+    BSS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    BSS_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    BSS_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *mean_ms = ms / (float)repeat;
+    return BSS_OK;
+}
+
+}  // extern "C"

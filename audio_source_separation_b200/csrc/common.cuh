@@ -1,0 +1,239 @@
+// Shared device helpers: complex arithmetic, mbarrier + bulk-copy (TMA, UBLKCP) wrappers,
+// warp reductions and the per-warp streaming ring used by the bin-tile kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define BSS_WARP 32
+#define BSS_FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------ complex (fp32)
+typedef float2 cf;
+
+__device__ __forceinline__ cf cf_make(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float cf_abs2(cf a) { return fmaf(a.x, a.x, a.y * a.y); }
+// acc += a * b
+__device__ __forceinline__ void cf_fma(cf& acc, cf a, cf b) {
+    acc.x = fmaf(a.x, b.x, acc.x);
+    acc.x = fmaf(-a.y, b.y, acc.x);
+    acc.y = fmaf(a.x, b.y, acc.y);
+    acc.y = fmaf(a.y, b.x, acc.y);
+}
+
+// ------------------------------------------------------------------------------ mbarrier / bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global bulk copy
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------ warp reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BSS_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BSS_FULL, v, o);
+    return v;
+}
+
+// Butterfly reduce-scatter of MP (= 32*Q) per-lane values: afterwards lane L holds in v[0..Q) the
+// warp-wide sums of elements Q*L .. Q*L+Q-1.  31*Q shuffles instead of 5*MP.
+template <int MP>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[MP], int lane) {
+    static_assert(MP % 32 == 0, "pad to a multiple of 32");
+#pragma unroll
+    for (int lvl = 0; lvl < 5; ++lvl) {
+        const int off = 16 >> lvl;
+        const int cnt = (MP / 2) >> lvl;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+            const float lo = v[i], hi = v[i + cnt];
+            const float send = up ? lo : hi;
+            const float keep = up ? hi : lo;
+            v[i] = keep + __shfl_xor_sync(BSS_FULL, send, off);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ streaming ring
+// A warp walks a list of jobs (bin tile, frame slab); lane 0 keeps STAGES-1 bulk copies in
+// flight into the warp's private shared-memory ring while the whole warp consumes the oldest.
+struct TileGeom {
+    int n_rows;        // rows per bin tile (channels or sources)
+    int row_len;       // padded frames per row in global memory (Tp)
+    int slab;          // frames per slab (== row_len when the tile is taken whole)
+    int n_slabs;       // slabs per tile
+    int row_stride;    // frames between rows inside a stage
+    uint32_t stage_bytes;
+};
+
+struct JobCursor {
+    long long item;    // flat item index
+    int slab;
+    __device__ __forceinline__ void advance(long long stride, int n_slabs) {
+        if (++slab == n_slabs) {
+            slab = 0;
+            item += stride;
+        }
+    }
+};
+
+__device__ __forceinline__ int slab_frames(const TileGeom& g, int slab) {
+    const int rest = g.row_len - slab * g.slab;
+    return rest < g.slab ? rest : g.slab;
+}
+
+// issue the copies of one job; `tile` points at row 0, frame 0 of the bin tile in global memory
+__device__ __forceinline__ void ring_issue(const TileGeom& g, const cf* tile, int slab, unsigned char* stage,
+                                           uint64_t* bar) {
+    if (g.n_slabs == 1) {
+        const uint32_t bytes = (uint32_t)g.n_rows * (uint32_t)g.row_len * 8u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage, tile, bytes, bar);
+    } else {
+        const int nf = slab_frames(g, slab);
+        const uint32_t bytes = (uint32_t)nf * 8u;
+        mbar_expect_tx(bar, bytes * (uint32_t)g.n_rows);
+        for (int r = 0; r < g.n_rows; ++r)
+            bulk_g2s(stage + (size_t)r * g.row_stride * 8, tile + (size_t)r * g.row_len + (size_t)slab * g.slab,
+                     bytes, bar);
+    }
+}
+
+// Per-warp stream over (item, slab) jobs.  Items owned by a warp are first, first+stride, ...;
+// the bin tile of an item is tile index item / items_per_tile.
+template <int STAGES>
+struct WarpStream {
+    TileGeom g;
+    uint64_t* bars;
+    unsigned char* ring;
+    const cf* base;
+    size_t tile_elems;
+    long long n_items, stride;
+    int items_per_tile;
+    JobCursor prod, cons;
+    int pstage, cstage, lane;
+    uint32_t cphase;
+
+    __device__ __forceinline__ void issue_next() {
+        if (prod.item < n_items) {
+            if (lane == 0)
+                ring_issue(g, base + (size_t)(prod.item / items_per_tile) * tile_elems, prod.slab,
+                           ring + (size_t)pstage * g.stage_bytes, &bars[pstage]);
+            prod.advance(stride, g.n_slabs);
+            pstage = (pstage + 1 == STAGES) ? 0 : pstage + 1;
+        }
+    }
+    __device__ __forceinline__ void start(const TileGeom& geom, uint64_t* bars_, unsigned char* ring_, const cf* base_,
+                                          long long first, long long stride_, long long n_items_, int items_per_tile_,
+                                          int lane_) {
+        g = geom;
+        bars = bars_;
+        ring = ring_;
+        base = base_;
+        tile_elems = (size_t)geom.n_rows * geom.row_len;
+        n_items = n_items_;
+        stride = stride_;
+        items_per_tile = items_per_tile_;
+        lane = lane_;
+        prod.item = cons.item = first;
+        prod.slab = cons.slab = 0;
+        pstage = cstage = 0;
+        cphase = 0;
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int s = 0; s < STAGES - 1; ++s) issue_next();
+    }
+    __device__ __forceinline__ bool active() const { return cons.item < n_items; }
+    // wait for the current job's tile; returns its shared-memory address
+    __device__ __forceinline__ const cf* acquire() {
+        mbar_wait(&bars[cstage], cphase);
+        return reinterpret_cast<const cf*>(ring + (size_t)cstage * g.stage_bytes);
+    }
+    __device__ __forceinline__ int frames() const { return slab_frames(g, cons.slab); }
+    __device__ __forceinline__ int frame0() const { return cons.slab * g.slab; }
+    __device__ __forceinline__ bool first_slab() const { return cons.slab == 0; }
+    __device__ __forceinline__ bool last_slab() const { return cons.slab == g.n_slabs - 1; }
+    // all lanes are done reading the current stage
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        cons.advance(stride, g.n_slabs);
+        if (++cstage == STAGES) {
+            cstage = 0;
+            cphase ^= 1u;
+        }
+    }
+};
+
+// host-side geometry of a [rows][Tp] bin tile: whole when small, 256-frame slabs otherwise
+#define BSS_SLAB_FRAMES 256
+#define BSS_WHOLE_TILE_BYTES 8192
+static inline TileGeom make_tile_geom(int rows, int Tp) {
+    TileGeom g;
+    g.n_rows = rows;
+    g.row_len = Tp;
+    if ((size_t)rows * Tp * 8 <= BSS_WHOLE_TILE_BYTES) {
+        g.slab = Tp;
+        g.n_slabs = 1;
+        g.row_stride = Tp;
+    } else {
+        g.slab = BSS_SLAB_FRAMES;
+        g.n_slabs = (Tp + BSS_SLAB_FRAMES - 1) / BSS_SLAB_FRAMES;
+        g.row_stride = BSS_SLAB_FRAMES;
+    }
+    g.stage_bytes = (uint32_t)(((size_t)rows * g.row_stride * 8 + 127) / 128 * 128);
+    return g;
+}

@@ -1,0 +1,231 @@
+// Internal definition of bss_handle: device-resident state of one batch of mixtures.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bssgpu.h"
+#include "common.cuh"
+
+// Device layouts (B = batch, Tp = n_frames rounded up to an even number so every frame row is a
+// multiple of 16 bytes -- the granule of cp.async.bulk; pad frames hold zeros):
+//   X     cf      [B][F][C][Tp]     mixture, bin-major: one bin tile (C rows) is contiguous
+//   Y     cf      [B][F][N][Tp]     estimates (ISS state / scratch), same tiling
+//   W     double2 [B][F][N][C]      demixing filters (FastMNMF: diagonaliser Q)
+//   basis float   [B][N][F][K]      ([B][F][K] when partitioned)
+//   act   float   [B][N][K][Tp]     ([B][K][Tp] when partitioned)
+//   U     double  [B][NW][F][C*C]   packed Hermitian weighted covariances (diag, then lower (re,im))
+//   Cx    double  [B][F][C*C]       packed plain covariance mean_t x x^H
+struct bss_handle {
+    bss_config cfg{};
+    int B = 1, C = 0, N = 0, F = 0, T = 0, Tp = 0, K = 0;
+    int n_sm = 148;
+    int max_smem = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    std::string err;
+
+    bool has_input = false;
+    bool has_filter = false;      // W holds a valid demixing filter (false for ISS between updates)
+    bool y_valid = false;         // Y buffer holds separate(X, W) / the ISS state
+    int pair_m = -1, pair_n = -1; // IP2 pair
+    bool pair_started = false;
+
+    cf* X = nullptr;
+    cf* Y = nullptr;
+    double2* W = nullptr;
+    float* basis = nullptr;
+    float* act = nullptr;
+    float* basis2 = nullptr;       // double buffer of basis (the basis update reads all K of the old one)
+    cf* Wf = nullptr;              // [B][F][N][C] fp32 mirror of W for the streaming kernels
+    float* latent = nullptr;       // [B][N][K]
+    double* U = nullptr;
+    double* Cx = nullptr;
+    int32_t* gate = nullptr;       // [B][N][F]
+    int32_t* flags = nullptr;      // [0] singular-bin counter
+    double* pw = nullptr;          // [B][N][F] per-bin source power (normalisation)
+    double* scale = nullptr;       // [B][N][F] complex (projection back)  -> 2 doubles each
+    float* wfr = nullptr;          // [B][N][Tp] AuxIVA frame weights (inverse, floored)
+    float* wraw = nullptr;         // [B][N][Tp] AuxIVA frame weights (raw)
+    int32_t* order = nullptr;      // [B][F][2] IP2 eigenvalue order
+    double* logdet = nullptr;      // [B][F]
+    double* aux = nullptr;         // [B][N] power-normalisation factors of the last update
+    double2* G2 = nullptr;         // [B][F][N][C] cross covariance Y X^H / T (ISS filter recovery)
+    float* part = nullptr;         // partial sums of the cross-bin reductions
+    size_t part_elems = 0;
+    float* iw = nullptr;           // [B][F][NW][Tp] explicit inverse weights (generic covariance path)
+    double* lossbuf = nullptr;     // [B][F] per-bin loss terms + [B] results
+    void* staging = nullptr;       // device staging for host <-> device layout conversion
+    size_t staging_bytes = 0;
+    void* pinned = nullptr;        // pinned host bounce buffer
+    size_t pinned_bytes = 0;
+
+    float* latent2 = nullptr;      // scratch for the partitioned latent update
+    // FastMNMF
+    float* G = nullptr;            // [B][N][F][M]
+    float* xt = nullptr;           // [B][F][M][Tp] |Q x|^2
+    float* mn_acc = nullptr;       // numerator / denominator accumulators
+    float* mn_acc2 = nullptr;
+    // NMF
+    float* target = nullptr;       // [B][F][Tp]
+};
+
+#define BSS_CUDA(h, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            return BSS_ECUDA;                                                                          \
+        }                                                                                              \
+    } while (0)
+
+#define BSS_TRY(expr)                    \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != BSS_OK) return rc__; \
+    } while (0)
+
+static inline int bss_fail(bss_handle* h, int code, const std::string& msg) {
+    h->err = msg;
+    return code;
+}
+
+static inline int ensure_staging(bss_handle* h, size_t bytes) {
+    if (bytes <= h->staging_bytes) return BSS_OK;
+    if (h->staging) cudaFree(h->staging);
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    BSS_CUDA(h, cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    return BSS_OK;
+}
+
+static inline int ensure_pinned(bss_handle* h, size_t bytes) {
+    if (bytes <= h->pinned_bytes) return BSS_OK;
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr;
+    h->pinned_bytes = 0;
+    BSS_CUDA(h, cudaMallocHost(&h->pinned, bytes));
+    h->pinned_bytes = bytes;
+    return BSS_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// Shared-memory plan of a warp-stream kernel: [wpc][stages] mbarriers | [wpc] scratch | [wpc][stages] stages
+struct StreamPlan {
+    int wpc;
+    uint32_t scratch_off, scratch_stride, ring_off;
+    size_t smem_bytes;
+    unsigned grid;
+};
+static inline bool plan_stream(const bss_handle* h, const TileGeom& g, int stages, size_t scratch_per_warp,
+                               long long n_items, int max_wpc, StreamPlan* out) {
+    const uint32_t scratch_stride = (uint32_t)round_up((int)scratch_per_warp, 16);
+    const size_t per_warp = (size_t)stages * g.stage_bytes + scratch_stride + (size_t)stages * 8;
+    int wpc = (int)(((size_t)h->max_smem - 512) / per_warp);
+    if (wpc > max_wpc) wpc = max_wpc;
+    if (wpc < 1) return false;
+    const uint32_t bars_bytes = (uint32_t)round_up(wpc * stages * 8, 128);
+    out->wpc = wpc;
+    out->scratch_off = bars_bytes;
+    out->scratch_stride = scratch_stride;
+    out->ring_off = (uint32_t)round_up((int)(bars_bytes + wpc * scratch_stride), 128);
+    out->smem_bytes = out->ring_off + (size_t)wpc * stages * g.stage_bytes;
+    int ctas_per_sm = (int)((size_t)h->max_smem / (out->smem_bytes + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const int by_threads = 2048 / (wpc * 32);
+    if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    long long grid = cdiv(n_items, wpc);
+    const long long cap = (long long)h->n_sm * ctas_per_sm;
+    if (grid > cap) grid = cap;
+    out->grid = (unsigned)grid;
+    return true;
+}
+
+// kernels_*.cu launchers -------------------------------------------------------------------------
+// weight modes of the covariance-accumulate kernel
+enum { WM_UNIT = 0, WM_ILRMA = 1, WM_FRAME = 2, WM_EXPLICIT = 3 };
+
+struct CovArgs {
+    const cf* X;          // [B][F][C][Tp]
+    double* U;            // [B][NW][F][C*C]
+    int B, F, C, NW, T, Tp;
+    int wmode;
+    // WM_ILRMA
+    const float* basis;   // [B][N][F][K]
+    const float* act;     // [B][N][K][Tp]
+    int K;
+    float expo;           // 2/domain
+    float eps;
+    // WM_FRAME
+    const float* wfr;     // [B][NW][Tp]  inverse weights
+    // WM_EXPLICIT
+    const float* iw;      // [B][F][NW][Tp] inverse weights
+    int wsel[8];          // weight sets to compute (IP2 computes only its pair)
+    int n_sel;
+};
+int launch_covariance(bss_handle* h, const CovArgs& a);
+
+struct IpArgs {
+    double2* W;           // [B][F][N][C]
+    const double* U;      // [B][NW][F][C*C]
+    const double* Cx;     // [B][F][C*C]  (may be null)
+    int32_t* gate;        // [B][N][F]     (may be null)
+    double* pw;           // [B][N][F]     (may be null): w_n^H Cx w_n after the sweep
+    int32_t* flags;
+    int B, F, C;
+    double threshold, eps;
+    int use_gate, floor_den;
+    int pair_m, pair_n;   // >= 0: IP2 update of this pair instead of the full sweep
+    int32_t* order;       // [B][F][2] IP2 eigenvalue order (may be null)
+    cf* Wf;               // [B][F][N][C] fp32 mirror of W kept for the streaming kernels (may be null)
+};
+int launch_ip(bss_handle* h, const IpArgs& a);
+int launch_pb_scale(bss_handle* h, const double2* W, const double* Cx, double2* scale, int B, int F, int C, int ref);
+int launch_logdet(bss_handle* h, const double2* W, double* out, long long n_bins, int C, int transpose_sq);
+int launch_lsq_filter(bss_handle* h, const double2* G, const double* Cx, double2* W, long long n_bins, int C);
+
+struct MuArgs {
+    const cf* X;          // [B][F][C][Tp]
+    const cf* Y;          // [B][F][N][Tp]; non-null: take |Y|^2 from the stored estimates (ISS)
+    const cf* Wf;         // [B][F][N][C]
+    const float* basis;   // [B][N][F][K]
+    float* basis_out;
+    const float* act;     // [B][N][K][Tp]
+    int B, F, C, T, Tp, K;
+    int mode;             // 0 Gauss (IS divergence), 1 Student-t
+    float p_exp, q_exp;   // (d+2)/d and d/(d+2)
+    float nu, eps;
+    int sel_m, sel_n;     // >= 0: pairwise source model, only these two sources move
+};
+int launch_mu_basis(bss_handle* h, const MuArgs& a);
+int launch_mu_act(bss_handle* h, const MuArgs& a, float* act);
+int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, const double* pw, int B, int N, int C, int F, int K,
+                           double domain, double eps, double* aux_out);
+int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const double2* scale, int B, int N, int C, int F, int K,
+                        double domain);
+int launch_sync_wf(bss_handle* h, const double2* W, cf* Wf, long long n);
+int launch_separate(bss_handle* h, const cf* X, const cf* Wf, const double2* scale, cf* Y, cf* out, int B, int C, int F, int T,
+                    int Tp);
+int launch_export_y(bss_handle* h, const cf* Y, const double2* scale, cf* out, int B, int N, int F, int T, int Tp);
+int launch_ilrma_loss(bss_handle* h, const MuArgs& a, float expo, double* terms);
+int launch_loss_finish(bss_handle* h, const double* terms, const double* logdet, double coef, int B, int F, double* out);
+int launch_import_x(bss_handle* h, const void* staged, int dtype, cf* X, int B, int C, int F, int T, int Tp);
+int launch_frame_weights(bss_handle* h, const cf* src, const cf* Wf, int from_y, float* winv, float* raw, int B, int C, int F,
+                         int T, int Tp, int kind, float eps);
+int launch_t_weights(bss_handle* h, const cf* X, const cf* Wf, const float* basis, const float* act, float* iw, int B, int C,
+                     int F, int K, int Tp, float nu, float eps);
+int launch_import_weights(bss_handle* h, const double* r_dev, float* iw, int N, int F, int T, int Tp);
+int launch_iss(bss_handle* h, cf* Y, int mode, const float* basis, const float* act, const float* wfr, double* pw, int B, int N,
+               int F, int T, int Tp, int K, float expo, float eps);
+int launch_cross_cov(bss_handle* h, const cf* Y, const cf* X, double2* G, long long n_bins, int C, int T, int Tp);
+int launch_scale_y(bss_handle* h, cf* Y, float* basis, const double* aux, const double2* scale, int B, int N, int F, int Tp, int K,
+                   double domain);
+int launch_aux_from_power(bss_handle* h, const double* pw, double* aux, int B, int N, int F, double eps);
+int launch_sum_frames(bss_handle* h, const float* raw, int B, int N, int T, int Tp, int kind, double coef, double eps, double* out);

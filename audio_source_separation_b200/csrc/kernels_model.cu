@@ -1,0 +1,838 @@
+// Source-model kernels of the ILRMA family and the kernels around them:
+//   - multiplicative update of the NMF basis T (per-bin reductions over frames)        src/bss/ilrma.py:413-419, :915-927
+//   - multiplicative update of the activation V (cross-bin reduction, two stages)      src/bss/ilrma.py:422-428, :929-938
+//   - power normalisation                                                             src/bss/ilrma.py:304-322
+//   - demixing Y = W X                                                                 src/bss/ilrma.py:153-165
+//   - negative log-likelihood                                                          src/bss/ilrma.py:648-677, :993-1020
+// The estimates Y = W X are never stored by the update loop: every consumer recomputes them from
+// the bin tile it has just staged.
+#include "handle.h"
+
+namespace {
+
+constexpr int MU_STAGES = 3;
+
+// a = dL/d(1/TV)-like numerator statistic, b = 1/TV   (TV already floored)
+__device__ __forceinline__ void mu_stats(int mode, float P, float tv, float p_exp, float nu, float& a, float& b) {
+    b = __frcp_rn(tv);
+    if (mode == 0) {
+        // Gauss / IS:  P / TV^p
+        if (p_exp == 2.f)
+            a = P * b * b;
+        else
+            a = P / powf(tv, p_exp);
+    } else {
+        // Student-t: h / TV^2,  h = 1 / (2/((2+nu) TV) + nu/((2+nu) P))    src/bss/ilrma.py:922
+        const float c = 2.f + nu;
+        const float h = 1.f / (2.f / (c * tv) + nu / (c * P));
+        a = h * b * b;
+    }
+}
+
+__device__ __forceinline__ float pow_q(float r, float q) { return q == 0.5f ? sqrtf(r) : powf(r, q); }
+
+template <int C, bool FROM_Y>
+__device__ __forceinline__ void load_filter(cf (&w)[C][C], const cf* Wf) {
+    if (!FROM_Y) {
+#pragma unroll
+        for (int n = 0; n < C; ++n)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[n][c] = __ldg(Wf + n * C + c);
+    }
+}
+
+// power of the estimates for two consecutive frames held in xv (float4 = 2 complex frames per row)
+template <int C, bool FROM_Y>
+__device__ __forceinline__ void frame_power(const float4 (&xv)[C], const cf (&w)[C][C], float (&P0)[C], float (&P1)[C]) {
+#pragma unroll
+    for (int n = 0; n < C; ++n) {
+        if (FROM_Y) {
+            P0[n] = fmaf(xv[n].x, xv[n].x, xv[n].y * xv[n].y);
+            P1[n] = fmaf(xv[n].z, xv[n].z, xv[n].w * xv[n].w);
+        } else {
+            cf y0 = cf_make(0.f, 0.f), y1 = cf_make(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                cf_fma(y0, w[n][c], cf_make(xv[c].x, xv[c].y));
+                cf_fma(y1, w[n][c], cf_make(xv[c].z, xv[c].w));
+            }
+            P0[n] = cf_abs2(y0);
+            P1[n] = cf_abs2(y1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- basis
+struct MuParams {
+    MuArgs a;
+    TileGeom g;
+    long long n_items;
+    int n_kc;
+    uint32_t scratch_off, scratch_stride, ring_off;
+};
+
+template <int C, int KC, bool FROM_Y>
+__global__ void __launch_bounds__(256) mu_basis_kernel(const MuParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MuArgs& a = p.a;
+    constexpr int N = C;
+    constexpr int M = N * KC * 2;
+    constexpr int MP = (M + 31) / 32 * 32;
+    constexpr int Q = MP / 32;
+    const int K = a.K;
+
+    float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);   // [N][K]
+    float* red = tb + N * K;                                                                        // [MP]
+    WarpStream<MU_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
+             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
+             (long long)blockIdx.x * wpc + warp, (long long)gridDim.x * wpc, p.n_items, p.n_kc, lane);
+    const int row_stride = p.g.row_stride;
+
+    float acc[MP];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) acc[i] = 0.f;
+    cf w[C][C];
+
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        const long long bf = st.cons.item / p.n_kc;
+        const int kc = (int)(st.cons.item - bf * p.n_kc);
+        const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
+        const int k0 = kc * KC;
+
+        if (st.first_slab()) {
+            for (int i = lane; i < N * K; i += 32) {
+                const int n = i / K, k = i - n * K;
+                tb[i] = a.basis[(((size_t)b * N + n) * a.F + f) * K + k];
+            }
+            load_filter<C, FROM_Y>(w, a.Wf + (size_t)bf * C * C);
+            __syncwarp();
+        }
+
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            float P0[C], P1[C];
+            frame_power<C, FROM_Y>(xv, w, P0, P1);
+            const int t = tbase + tt;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const float* v = a.act + ((size_t)b * N + n) * K * a.Tp + t;
+                float tv0 = 0.f, tv1 = 0.f;
+                float2 vk[KC];
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) vk[kk] = make_float2(0.f, 0.f);
+                for (int k = 0; k < K; ++k) {
+                    const float2 vv = __ldg(reinterpret_cast<const float2*>(v + (size_t)k * a.Tp));
+                    const float tk = tb[n * K + k];
+                    tv0 = fmaf(tk, vv.x, tv0);
+                    tv1 = fmaf(tk, vv.y, tv1);
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk)
+                        if (k == k0 + kk) vk[kk] = vv;
+                }
+                tv0 = tv0 < a.eps ? a.eps : tv0;
+                tv1 = tv1 < a.eps ? a.eps : tv1;
+                float a0, b0, a1, b1;
+                mu_stats(a.mode, P0[n], tv0, a.p_exp, a.nu, a0, b0);
+                mu_stats(a.mode, P1[n], tv1, a.p_exp, a.nu, a1, b1);
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) {
+                    float& num = acc[(n * KC + kk) * 2];
+                    float& den = acc[(n * KC + kk) * 2 + 1];
+                    num = fmaf(a0, vk[kk].x, num);
+                    num = fmaf(a1, vk[kk].y, num);
+                    den = fmaf(b0, vk[kk].x, den);
+                    den = fmaf(b1, vk[kk].y, den);
+                }
+            }
+        }
+
+        if (st.last_slab()) {
+            warp_reduce_scatter<MP>(acc, lane);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) red[Q * lane + q] = acc[q];
+            __syncwarp();
+            for (int i = lane; i < N * KC; i += 32) {
+                const int n = i / KC, kk = i - n * KC, k = k0 + kk;
+                if (k < K) {
+                    const float num = red[2 * i];
+                    float den = red[2 * i + 1];
+                    den = den < a.eps ? a.eps : den;
+                    const float told = tb[n * K + k];
+                    const bool sel = a.sel_m < 0 || n == a.sel_m || n == a.sel_n;
+                    a.basis_out[(((size_t)b * N + n) * a.F + f) * K + k] = sel ? told * pow_q(num / den, a.q_exp) : told;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MP; ++i) acc[i] = 0.f;
+        }
+        st.release();
+    }
+}
+
+template <int C, int KC, bool FROM_Y>
+int launch_mu_basis_t(bss_handle* h, const MuArgs& a) {
+    MuParams p;
+    p.a = a;
+    p.g = make_tile_geom(C, a.Tp);
+    p.n_kc = (a.K + KC - 1) / KC;
+    p.n_items = (long long)a.B * a.F * p.n_kc;
+    constexpr int MP = (C * KC * 2 + 31) / 32 * 32;
+    StreamPlan sp;
+    if (!plan_stream(h, p.g, MU_STAGES, ((size_t)C * a.K + MP) * 4, p.n_items, 8, &sp))
+        return bss_fail(h, BSS_EINVAL, "source model: frame tile does not fit in shared memory");
+    p.scratch_off = sp.scratch_off;
+    p.scratch_stride = sp.scratch_stride;
+    p.ring_off = sp.ring_off;
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->max_smem));
+        attr_done = true;
+    }
+    mu_basis_kernel<C, KC, FROM_Y><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+// ------------------------------------------------------------------------------------------- activation
+// Stage 1: a warp owns 64 frames (two per lane) of one mixture and walks a chunk of bins, reading
+// the 512-byte row segments straight from global memory; partial sums go to `part`.
+// part layout: [B][n_chunks][N][K][2][Tp]
+template <int C, int KC, bool FROM_Y>
+__global__ void __launch_bounds__(128) mu_act_partial_kernel(const MuArgs a, float* part, int n_chunks, int bins_per_chunk,
+                                                            int n_slabs, int n_kc, long long n_items) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const long long item = (long long)blockIdx.x * wpc + warp;
+    if (item >= n_items) return;
+    constexpr int N = C;
+    const int K = a.K;
+    // item -> (b, chunk, slab, kc), kc fastest so that the k-chunks of a tile run side by side
+    long long r = item;
+    const int kc = (int)(r % n_kc);
+    r /= n_kc;
+    const int slab = (int)(r % n_slabs);
+    r /= n_slabs;
+    const int chunk = (int)(r % n_chunks);
+    const int b = (int)(r / n_chunks);
+    const int k0 = kc * KC;
+    const int t0 = slab * 64 + 2 * lane;
+    const bool live = t0 < a.Tp;
+
+    // activation slab of this warp: vs[n][k][64]
+    float* vs = reinterpret_cast<float*>(smem) + (size_t)warp * N * K * 64;
+    for (int i = 0; i < N * K; ++i) {
+        float2 vv = make_float2(0.f, 0.f);
+        if (live) vv = __ldg(reinterpret_cast<const float2*>(a.act + ((size_t)b * N * K + i) * a.Tp + t0));
+        *reinterpret_cast<float2*>(vs + (size_t)i * 64 + 2 * lane) = vv;
+    }
+    __syncwarp();
+
+    float num0[N][KC], num1[N][KC], den0[N][KC], den1[N][KC];
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) num0[n][kk] = num1[n][kk] = den0[n][kk] = den1[n][kk] = 0.f;
+
+    const int f_begin = chunk * bins_per_chunk;
+    const int f_end = min(a.F, f_begin + bins_per_chunk);
+    const cf* src = FROM_Y ? a.Y : a.X;
+#pragma unroll 1
+    for (int f = f_begin; f < f_end; ++f) {
+        const size_t bf = (size_t)b * a.F + f;
+        float4 xv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(src + (bf * C + c) * a.Tp + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cf w[C][C];
+        load_filter<C, FROM_Y>(w, a.Wf + bf * C * C);
+        float P0[C], P1[C];
+        frame_power<C, FROM_Y>(xv, w, P0, P1);
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            const float* tbn = a.basis + ((size_t)b * N + n) * a.F * K + (size_t)f * K;
+            float tv0 = 0.f, tv1 = 0.f;
+            float tk[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) tk[kk] = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float tkv = __ldg(tbn + k);
+                const float2 vv = *reinterpret_cast<const float2*>(vs + ((size_t)n * K + k) * 64 + 2 * lane);
+                tv0 = fmaf(tkv, vv.x, tv0);
+                tv1 = fmaf(tkv, vv.y, tv1);
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk)
+                    if (k == k0 + kk) tk[kk] = tkv;
+            }
+            tv0 = tv0 < a.eps ? a.eps : tv0;
+            tv1 = tv1 < a.eps ? a.eps : tv1;
+            float a0, b0, a1, b1;
+            mu_stats(a.mode, P0[n], tv0, a.p_exp, a.nu, a0, b0);
+            mu_stats(a.mode, P1[n], tv1, a.p_exp, a.nu, a1, b1);
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                num0[n][kk] = fmaf(tk[kk], a0, num0[n][kk]);
+                num1[n][kk] = fmaf(tk[kk], a1, num1[n][kk]);
+                den0[n][kk] = fmaf(tk[kk], b0, den0[n][kk]);
+                den1[n][kk] = fmaf(tk[kk], b1, den1[n][kk]);
+            }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int k = k0 + kk;
+            if (k < K) {
+                float* dst = part + (((((size_t)b * n_chunks + chunk) * N + n) * K + k) * 2) * a.Tp + t0;
+                *reinterpret_cast<float2*>(dst) = make_float2(num0[n][kk], num1[n][kk]);
+                *reinterpret_cast<float2*>(dst + a.Tp) = make_float2(den0[n][kk], den1[n][kk]);
+            }
+        }
+}
+
+// Stage 2: fixed-order sum over the chunks (deterministic), then V <- V (num/den)^q, in place.
+__global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, const float* part, float* act, int N, int n_chunks) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)a.B * N * a.K * a.Tp;
+    if (idx >= total) return;
+    const int t = (int)(idx % a.Tp);
+    long long r = idx / a.Tp;
+    const int k = (int)(r % a.K);
+    r /= a.K;
+    const int n = (int)(r % N);
+    const int b = (int)(r / N);
+    if (t >= a.T) {
+        act[idx] = 0.f;
+        return;
+    }
+    const bool sel = a.sel_m < 0 || n == a.sel_m || n == a.sel_n;
+    if (!sel) return;
+    float num = 0.f, den = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+        const float* src = part + (((((size_t)b * n_chunks + c) * N + n) * a.K + k) * 2) * a.Tp + t;
+        num += src[0];
+        den += src[a.Tp];
+    }
+    den = den < a.eps ? a.eps : den;
+    act[idx] = act[idx] * pow_q(num / den, a.q_exp);
+}
+
+template <int C, int KC, bool FROM_Y>
+int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act) {
+    const int n_kc = (a.K + KC - 1) / KC;
+    const int n_slabs = (a.Tp + 63) / 64;
+    // enough warps to fill the machine a few times over, but chunks of at least 4 bins
+    long long want = (long long)h->n_sm * 24;
+    long long per_chunk_items = (long long)a.B * n_slabs * n_kc;
+    int n_chunks = (int)cdiv(want, per_chunk_items);
+    if (n_chunks < 1) n_chunks = 1;
+    int bins_per_chunk = (int)cdiv(a.F, n_chunks);
+    if (bins_per_chunk < 4) bins_per_chunk = a.F < 4 ? a.F : 4;
+    n_chunks = (int)cdiv(a.F, bins_per_chunk);
+    const size_t need = (size_t)a.B * n_chunks * C * a.K * 2 * a.Tp;
+    if (need > h->part_elems) {
+        if (h->part) cudaFree(h->part);
+        h->part = nullptr;
+        BSS_CUDA(h, cudaMalloc(&h->part, need * sizeof(float)));
+        h->part_elems = need;
+    }
+    const long long n_items = per_chunk_items * n_chunks;
+    const int wpc = 4;
+    const size_t smem_bytes = (size_t)wpc * C * a.K * 64 * sizeof(float);
+    if (smem_bytes > (size_t)h->max_smem) return bss_fail(h, BSS_EINVAL, "source model: n_basis too large");
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_partial_kernel<C, KC, FROM_Y>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        attr_done = true;
+    }
+    mu_act_partial_kernel<C, KC, FROM_Y><<<(unsigned)cdiv(n_items, wpc), wpc * 32, smem_bytes, h->stream>>>(
+        a, h->part, n_chunks, bins_per_chunk, n_slabs, n_kc, n_items);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    const long long total = (long long)a.B * C * a.K * a.Tp;
+    mu_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, act, C, n_chunks);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+// ------------------------------------------------------------------------------------------- normalisation
+// aux_n = max(sqrt(mean_f pw[n,f]), eps);  W[:,n,:] /= aux_n;  T[n] /= aux_n^domain     src/bss/ilrma.py:305-322
+// grid (blocks_per_mixture, B); every block recomputes the N scalars (deterministic, fp64).
+__global__ void __launch_bounds__(256) normalize_power_kernel(double2* W, cf* Wf, float* basis, const double* pw, int N, int C,
+                                                              int F, int K, double domain, double eps, double* aux_out) {
+    __shared__ double red[8][8];
+    __shared__ double aux_s[8];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = 0; n < N; ++n) {
+        double s = 0.0;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) s += pw[((size_t)b * N + n) * F + f];
+        s = warp_sum(s);
+        if (lane == 0) red[n][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+        double aux = sqrt(s / (double)F);
+        if (aux < eps) aux = eps;
+        aux_s[threadIdx.x] = aux;
+        if (blockIdx.x == 0 && aux_out) aux_out[(size_t)b * N + threadIdx.x] = aux;
+    }
+    __syncthreads();
+    const long long nW = (long long)F * N * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)((i / C) % N);
+        const double inv = 1.0 / aux_s[n];
+        double2 v = W[(size_t)b * nW + i];
+        v.x *= inv;
+        v.y *= inv;
+        W[(size_t)b * nW + i] = v;
+        Wf[(size_t)b * nW + i] = cf_make((float)v.x, (float)v.y);
+    }
+    if (basis) {
+        const long long nT = (long long)N * F * K;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nT; i += (long long)gridDim.x * blockDim.x) {
+            const int n = (int)(i / ((long long)F * K));
+            const double sc = domain == 2.0 ? aux_s[n] * aux_s[n] : pow(aux_s[n], domain);
+            basis[(size_t)b * nT + i] = (float)((double)basis[(size_t)b * nT + i] / sc);
+        }
+    }
+}
+
+// W[f,n,:] *= scale[n,f];  T[n,f,:] *= |scale[n,f]|^domain     src/bss/ilrma.py:323-330
+__global__ void __launch_bounds__(256) normalize_pb_kernel(double2* W, cf* Wf, float* basis, const double2* scale, int B, int N,
+                                                           int C, int F, int K, double domain) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * F * N) return;
+    const int n = (int)(idx % N);
+    const long long bf = idx / N;
+    const int f = (int)(bf % F);
+    const int b = (int)(bf / F);
+    const double2 s = scale[((size_t)b * N + n) * F + f];
+    for (int c = 0; c < C; ++c) {
+        const double2 v = W[(size_t)idx * C + c];
+        const double2 r = make_double2(v.x * s.x - v.y * s.y, v.x * s.y + v.y * s.x);
+        W[(size_t)idx * C + c] = r;
+        Wf[(size_t)idx * C + c] = cf_make((float)r.x, (float)r.y);
+    }
+    if (basis) {
+        const double m = hypot(s.x, s.y);
+        const double sc = domain == 2.0 ? m * m : pow(m, domain);
+        for (int k = 0; k < K; ++k) {
+            float* p = basis + (((size_t)b * N + n) * F + f) * K + k;
+            *p = (float)((double)*p * sc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sync_wf_kernel(const double2* W, cf* Wf, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Wf[i] = cf_make((float)W[i].x, (float)W[i].y);
+}
+
+// ------------------------------------------------------------------------------------------- demixing
+struct SepParams {
+    const cf* X;
+    const cf* Wf;
+    const double2* scale;   // [B][N][F] or null
+    cf* Y;                  // [B][F][N][Tp] or null
+    cf* out;                // [B][N][F][T]  or null (reference layout)
+    int B, F, T, Tp;
+    TileGeom g;
+    long long n_items;
+    uint32_t scratch_off, scratch_stride, ring_off;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    WarpStream<MU_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
+             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, p.X, (long long)blockIdx.x * wpc + warp,
+             (long long)gridDim.x * wpc, p.n_items, 1, lane);
+    const int row_stride = p.g.row_stride;
+    cf w[C][C];
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        const long long bf = st.cons.item;
+        const int b = (int)(bf / p.F), f = (int)(bf - (long long)b * p.F);
+        if (st.first_slab()) {
+            load_filter<C, false>(w, p.Wf + (size_t)bf * C * C);
+            if (p.scale) {
+#pragma unroll
+                for (int n = 0; n < C; ++n) {
+                    const double2 sd = p.scale[((size_t)b * C + n) * p.F + f];
+                    const cf s = cf_make((float)sd.x, (float)sd.y);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const cf v = w[n][c];
+                        w[n][c] = cf_make(v.x * s.x - v.y * s.y, v.x * s.y + v.y * s.x);
+                    }
+                }
+            }
+        }
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            const int t = tbase + tt;
+#pragma unroll
+            for (int n = 0; n < C; ++n) {
+                cf y0 = cf_make(0.f, 0.f), y1 = cf_make(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    cf_fma(y0, w[n][c], cf_make(xv[c].x, xv[c].y));
+                    cf_fma(y1, w[n][c], cf_make(xv[c].z, xv[c].w));
+                }
+                if (p.Y)
+                    *reinterpret_cast<float4*>(p.Y + ((size_t)bf * C + n) * p.Tp + t) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                if (p.out) {
+                    cf* o = p.out + (((size_t)b * C + n) * p.F + f) * p.T + t;
+                    if (t < p.T) o[0] = y0;
+                    if (t + 1 < p.T) o[1] = y1;
+                }
+            }
+        }
+        st.release();
+    }
+}
+
+// Y tile -> reference layout with optional per-(n,f) complex scale (ISS output path)
+__global__ void __launch_bounds__(256) export_y_kernel(const cf* Y, const double2* scale, cf* out, int B, int N, int F, int T, int Tp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * N * F * T) return;
+    const int t = (int)(idx % T);
+    long long r = idx / T;
+    const int f = (int)(r % F);
+    r /= F;
+    const int n = (int)(r % N);
+    const int b = (int)(r / N);
+    cf v = Y[(((size_t)b * F + f) * N + n) * Tp + t];
+    if (scale) {
+        const double2 sd = scale[((size_t)b * N + n) * F + f];
+        const cf s = cf_make((float)sd.x, (float)sd.y);
+        v = cf_make(v.x * s.x - v.y * s.y, v.x * s.y + v.y * s.x);
+    }
+    out[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------- loss
+// per bin: sum_{n,t} (P/R + log R)            (mode 0, src/bss/ilrma.py:669-676)
+//          sum_{n,t} ((1+nu/2) log(1 + (2/nu) P/R) + log R)   (mode 1, src/bss/ilrma.py:1012-1019)
+struct LossParams {
+    MuArgs a;
+    double* out;   // [B][F]
+    float expo;    // 2/domain
+    TileGeom g;
+    long long n_items;
+    uint32_t scratch_off, scratch_stride, ring_off;
+};
+
+template <int C, bool FROM_Y>
+__global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MuArgs& a = p.a;
+    constexpr int N = C;
+    const int K = a.K;
+    float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);
+    WarpStream<MU_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
+             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
+             (long long)blockIdx.x * wpc + warp, (long long)gridDim.x * wpc, p.n_items, 1, lane);
+    const int row_stride = p.g.row_stride;
+    cf w[C][C];
+    double total = 0.0;
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        const long long bf = st.cons.item;
+        const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
+        if (st.first_slab()) {
+            for (int i = lane; i < N * K; i += 32) {
+                const int n = i / K, k = i - n * K;
+                tb[i] = a.basis[(((size_t)b * N + n) * a.F + f) * K + k];
+            }
+            load_filter<C, FROM_Y>(w, a.Wf + (size_t)bf * C * C);
+            total = 0.0;
+            __syncwarp();
+        }
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+        float part = 0.f;
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            float P0[C], P1[C];
+            frame_power<C, FROM_Y>(xv, w, P0, P1);
+            const int t = tbase + tt;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const float* v = a.act + ((size_t)b * N + n) * K * a.Tp + t;
+                float r0 = 0.f, r1 = 0.f;
+                for (int k = 0; k < K; ++k) {
+                    const float2 vv = __ldg(reinterpret_cast<const float2*>(v + (size_t)k * a.Tp));
+                    const float tk = tb[n * K + k];
+                    r0 = fmaf(tk, vv.x, r0);
+                    r1 = fmaf(tk, vv.y, r1);
+                }
+                if (p.expo != 1.f) {
+                    r0 = powf(r0, p.expo);
+                    r1 = powf(r1, p.expo);
+                }
+                r0 = r0 < a.eps ? a.eps : r0;
+                r1 = r1 < a.eps ? a.eps : r1;
+                float l0, l1;
+                if (a.mode == 0) {
+                    l0 = P0[n] / r0 + logf(r0);
+                    l1 = P1[n] / r1 + logf(r1);
+                } else {
+                    l0 = (1.f + 0.5f * a.nu) * log1pf((2.f / a.nu) * (P0[n] / r0)) + logf(r0);
+                    l1 = (1.f + 0.5f * a.nu) * log1pf((2.f / a.nu) * (P1[n] / r1)) + logf(r1);
+                }
+                if (t < a.T) part += l0;
+                if (t + 1 < a.T) part += l1;
+            }
+        }
+        total += (double)part;
+        if (st.last_slab()) {
+            const double s = warp_sum(total);
+            if (lane == 0) p.out[bf] = s;
+        }
+        st.release();
+    }
+}
+
+// loss[b] = sum_f terms[b,f] - coef * sum_f logdet[b,f]   (fixed-order block reduction, fp64)
+__global__ void __launch_bounds__(256) loss_finish_kernel(const double* terms, const double* logdet, double coef, int F, double* out) {
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    double s = 0.0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        double v = 0.0;
+        if (terms) v += terms[(size_t)b * F + f];
+        if (logdet) v -= coef * logdet[(size_t)b * F + f];
+        s += v;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        out[b] += t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host <-> device layouts
+// host (B,C,F,T) complex{64,128} staged on the device -> X [B][F][C][Tp] complex64 (pad frames zeroed)
+template <typename TIn>
+__global__ void __launch_bounds__(256) import_x_kernel(const TIn* in, cf* X, int B, int C, int F, int T, int Tp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * F * C * Tp) return;
+    const int t = (int)(idx % Tp);
+    long long r = idx / Tp;
+    const int c = (int)(r % C);
+    r /= C;
+    const int f = (int)(r % F);
+    const int b = (int)(r / F);
+    cf v = cf_make(0.f, 0.f);
+    if (t < T) {
+        const TIn s = in[(((size_t)b * C + c) * F + f) * T + t];
+        v = cf_make((float)s.x, (float)s.y);
+    }
+    X[idx] = v;
+}
+
+}  // namespace
+
+#define BSS_DISPATCH_C(Cval, CALL)                                                     \
+    switch (Cval) {                                                                    \
+        case 2: { constexpr int CC_ = 2; CALL; } break;                                \
+        case 3: { constexpr int CC_ = 3; CALL; } break;                                \
+        case 4: { constexpr int CC_ = 4; CALL; } break;                                \
+        case 5: { constexpr int CC_ = 5; CALL; } break;                                \
+        case 6: { constexpr int CC_ = 6; CALL; } break;                                \
+        case 7: { constexpr int CC_ = 7; CALL; } break;                                \
+        case 8: { constexpr int CC_ = 8; CALL; } break;                                \
+        default: return bss_fail(h, BSS_EINVAL, "n_channels must be between 2 and 8"); \
+    }
+
+int launch_mu_basis(bss_handle* h, const MuArgs& a) {
+    int rc = BSS_OK;
+    const bool from_y = a.Y != nullptr;
+    if (a.K <= 2) {
+        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 2, true>(h, a))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 2, false>(h, a))) }
+    } else {
+        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 4, true>(h, a))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 4, false>(h, a))) }
+    }
+    return rc;
+}
+
+int launch_mu_act(bss_handle* h, const MuArgs& a, float* act) {
+    int rc = BSS_OK;
+    const bool from_y = a.Y != nullptr;
+    if (a.K <= 2) {
+        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, true>(h, a, act))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, false>(h, a, act))) }
+    } else {
+        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, true>(h, a, act))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, false>(h, a, act))) }
+    }
+    return rc;
+}
+
+int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, const double* pw, int B, int N, int C, int F, int K,
+                           double domain, double eps, double* aux_out) {
+    dim3 grid(8, B);
+    normalize_power_kernel<<<grid, 256, 0, h->stream>>>(W, Wf, basis, pw, N, C, F, K, domain, eps, aux_out);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const double2* scale, int B, int N, int C, int F, int K,
+                        double domain) {
+    const long long n = (long long)B * F * N;
+    normalize_pb_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(W, Wf, basis, scale, B, N, C, F, K, domain);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_sync_wf(bss_handle* h, const double2* W, cf* Wf, long long n) {
+    sync_wf_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(W, Wf, n);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+template <int C>
+static int launch_separate_t(bss_handle* h, const cf* X, const cf* Wf, const double2* scale, cf* Y, cf* out, int B, int F, int T,
+                             int Tp) {
+    SepParams p;
+    p.X = X;
+    p.Wf = Wf;
+    p.scale = scale;
+    p.Y = Y;
+    p.out = out;
+    p.B = B;
+    p.F = F;
+    p.T = T;
+    p.Tp = Tp;
+    p.g = make_tile_geom(C, Tp);
+    p.n_items = (long long)B * F;
+    StreamPlan sp;
+    if (!plan_stream(h, p.g, MU_STAGES, 16, p.n_items, 8, &sp))
+        return bss_fail(h, BSS_EINVAL, "separate: frame tile does not fit in shared memory");
+    p.scratch_off = sp.scratch_off;
+    p.scratch_stride = sp.scratch_stride;
+    p.ring_off = sp.ring_off;
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(separate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        attr_done = true;
+    }
+    separate_kernel<C><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_separate(bss_handle* h, const cf* X, const cf* Wf, const double2* scale, cf* Y, cf* out, int B, int C, int F, int T,
+                    int Tp) {
+    int rc = BSS_OK;
+    BSS_DISPATCH_C(C, (rc = launch_separate_t<CC_>(h, X, Wf, scale, Y, out, B, F, T, Tp)))
+    return rc;
+}
+
+int launch_export_y(bss_handle* h, const cf* Y, const double2* scale, cf* out, int B, int N, int F, int T, int Tp) {
+    const long long n = (long long)B * N * F * T;
+    export_y_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(Y, scale, out, B, N, F, T, Tp);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+template <int C, bool FROM_Y>
+static int launch_ilrma_loss_t(bss_handle* h, const MuArgs& a, float expo, double* terms) {
+    LossParams p;
+    p.a = a;
+    p.out = terms;
+    p.expo = expo;
+    p.g = make_tile_geom(C, a.Tp);
+    p.n_items = (long long)a.B * a.F;
+    StreamPlan sp;
+    if (!plan_stream(h, p.g, MU_STAGES, (size_t)C * a.K * 4, p.n_items, 8, &sp))
+        return bss_fail(h, BSS_EINVAL, "loss: frame tile does not fit in shared memory");
+    p.scratch_off = sp.scratch_off;
+    p.scratch_stride = sp.scratch_stride;
+    p.ring_off = sp.ring_off;
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(ilrma_loss_kernel<C, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->max_smem));
+        attr_done = true;
+    }
+    ilrma_loss_kernel<C, FROM_Y><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_ilrma_loss(bss_handle* h, const MuArgs& a, float expo, double* terms) {
+    int rc = BSS_OK;
+    if (a.Y) { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, true>(h, a, expo, terms))) }
+    else { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, false>(h, a, expo, terms))) }
+    return rc;
+}
+
+int launch_loss_finish(bss_handle* h, const double* terms, const double* logdet, double coef, int B, int F, double* out) {
+    loss_finish_kernel<<<B, 256, 0, h->stream>>>(terms, logdet, coef, F, out);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_import_x(bss_handle* h, const void* staged, int dtype, cf* X, int B, int C, int F, int T, int Tp) {
+    const long long n = (long long)B * F * C * Tp;
+    const unsigned grid = (unsigned)cdiv(n, 256);
+    if (dtype == BSS_C128)
+        import_x_kernel<double2><<<grid, 256, 0, h->stream>>>((const double2*)staged, X, B, C, F, T, Tp);
+    else
+        import_x_kernel<float2><<<grid, 256, 0, h->stream>>>((const float2*)staged, X, B, C, F, T, Tp);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}

@@ -1,0 +1,31 @@
+// Per-method orchestration (which kernels one update_once launches, in which order).
+#pragma once
+#include "handle.h"
+
+// determined BSS (ILRMA / AuxIVA): methods_bss.cu
+int bss_allocate(bss_handle* h);
+int bss_reset_filter(bss_handle* h);
+int ilrma_update_once(bss_handle* h);
+int tilrma_update_once(bss_handle* h);
+int auxiva_update_once(bss_handle* h);
+int bss_loss_device(bss_handle* h);                       // result in lossbuf[B*F .. B*F+B)
+int bss_separate_to(bss_handle* h, cf* out, int apply_pb); // out: device (B,N,F,T) complex64
+int bss_filter_from_estimates(bss_handle* h);
+int bss_covariance_only(bss_handle* h);
+int bss_refresh_estimates(bss_handle* h);                 // Y <- W X (bin-major device buffer)
+
+// GaussILRMA(partitioning=True): methods_part.cu
+int ilrma_partitioned_update_once(bss_handle* h);
+int ilrma_partitioned_loss(bss_handle* h);
+
+// FastMNMF: methods_mnmf.cu
+int mnmf_allocate(bss_handle* h);
+int mnmf_reset(bss_handle* h);
+int mnmf_update_once(bss_handle* h);
+int mnmf_loss(bss_handle* h);
+int mnmf_separate(bss_handle* h, cf* out);
+
+// single-channel NMF: methods_nmf.cu
+int nmf_allocate(bss_handle* h);
+int nmf_update_once(bss_handle* h);
+int nmf_loss(bss_handle* h);

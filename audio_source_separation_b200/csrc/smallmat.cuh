@@ -1,0 +1,306 @@
+// Per-bin dense complex linear algebra in fp64 registers (C x C, C <= 8).
+// Everything is __host__ __device__ so the same code is exercised on the CPU by
+// tests/hostmath (test harness only; the product calls these from kernels).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SM_HD __host__ __device__ __forceinline__
+#else
+#define SM_HD inline
+#endif
+
+struct cd {
+    double x, y;
+};
+SM_HD cd cd_make(double a, double b) {
+    cd r;
+    r.x = a;
+    r.y = b;
+    return r;
+}
+SM_HD cd operator+(cd a, cd b) { return cd_make(a.x + b.x, a.y + b.y); }
+SM_HD cd operator-(cd a, cd b) { return cd_make(a.x - b.x, a.y - b.y); }
+SM_HD cd operator*(cd a, cd b) { return cd_make(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+SM_HD cd operator*(double s, cd a) { return cd_make(s * a.x, s * a.y); }
+SM_HD cd cd_conj(cd a) { return cd_make(a.x, -a.y); }
+SM_HD double cd_abs2(cd a) { return a.x * a.x + a.y * a.y; }
+SM_HD double cd_abs(cd a) { return hypot(a.x, a.y); }
+// a / b, Smith's algorithm (what NumPy uses for complex division)
+SM_HD cd cd_div(cd a, cd b) {
+    if (fabs(b.x) >= fabs(b.y)) {
+        if (b.x == 0.0 && b.y == 0.0) return cd_make(a.x / fabs(b.x), a.y / fabs(b.x));
+        const double r = b.y / b.x, s = 1.0 / (b.x + b.y * r);
+        return cd_make((a.x + a.y * r) * s, (a.y - a.x * r) * s);
+    }
+    const double r = b.x / b.y, s = 1.0 / (b.x * r + b.y);
+    return cd_make((a.x * r + a.y) * s, (a.y * r - a.x) * s);
+}
+// principal square root
+SM_HD cd cd_sqrt(cd a) {
+    if (a.x == 0.0 && a.y == 0.0) return cd_make(0.0, a.y);
+    const double m = hypot(a.x, a.y);
+    if (a.x >= 0.0) {
+        const double t = sqrt(0.5 * (m + a.x));
+        return cd_make(t, a.y / (2.0 * t));
+    }
+    const double t = sqrt(0.5 * (m - a.x));
+    return cd_make(fabs(a.y) / (2.0 * t), a.y >= 0.0 ? t : -t);
+}
+// acc += a * b
+SM_HD void cd_fma(cd& acc, cd a, cd b) {
+    acc.x += a.x * b.x - a.y * b.y;
+    acc.y += a.x * b.y + a.y * b.x;
+}
+// NumPy orders complex numbers lexicographically (real, then imag): `den[den < eps] = eps`
+SM_HD bool cd_less_real(cd a, double e) { return a.x < e || (a.x == e && a.y < 0.0); }
+
+template <int C>
+struct Mat {
+    cd a[C][C];
+};
+
+template <int C>
+SM_HD void mat_mul(const Mat<C>& A, const Mat<C>& B, Mat<C>& R) {
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            cd s = cd_make(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < C; ++k) cd_fma(s, A.a[i][k], B.a[k][j]);
+            R.a[i][j] = s;
+        }
+}
+
+template <int C>
+SM_HD double mat_fro2(const Mat<C>& A) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) s += cd_abs2(A.a[i][j]);
+    return s;
+}
+
+// Gauss-Jordan inverse with partial pivoting.  Returns false on an exactly zero pivot
+// (LAPACK's `info > 0`, which NumPy turns into LinAlgError("Singular matrix")).
+template <int C>
+SM_HD bool mat_inverse(const Mat<C>& Ain, Mat<C>& Inv) {
+    Mat<C> A = Ain;
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) Inv.a[i][j] = cd_make(i == j ? 1.0 : 0.0, 0.0);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        // pivot search (LAPACK izamax uses |re| + |im|)
+        int p = k;
+        double best = fabs(A.a[k][k].x) + fabs(A.a[k][k].y);
+#pragma unroll
+        for (int i = k + 1; i < C; ++i) {
+            const double v = fabs(A.a[i][k].x) + fabs(A.a[i][k].y);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        if (best == 0.0) ok = false;
+        // row swap k <-> p (compile-time indices only: predicated exchange)
+#pragma unroll
+        for (int i = k + 1; i < C; ++i) {
+            if (i == p) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    cd t = A.a[k][j];
+                    A.a[k][j] = A.a[i][j];
+                    A.a[i][j] = t;
+                    t = Inv.a[k][j];
+                    Inv.a[k][j] = Inv.a[i][j];
+                    Inv.a[i][j] = t;
+                }
+            }
+        }
+        const cd piv = cd_div(cd_make(1.0, 0.0), A.a[k][k]);
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            A.a[k][j] = A.a[k][j] * piv;
+            Inv.a[k][j] = Inv.a[k][j] * piv;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            if (i == k) continue;
+            const cd f = A.a[i][k];
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                A.a[i][j] = A.a[i][j] - f * A.a[k][j];
+                Inv.a[i][j] = Inv.a[i][j] - f * Inv.a[k][j];
+            }
+        }
+    }
+    return ok;
+}
+
+template <int C>
+SM_HD cd mat_det(const Mat<C>& Ain) {
+    Mat<C> A = Ain;
+    cd det = cd_make(1.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        int p = k;
+        double best = fabs(A.a[k][k].x) + fabs(A.a[k][k].y);
+#pragma unroll
+        for (int i = k + 1; i < C; ++i) {
+            const double v = fabs(A.a[i][k].x) + fabs(A.a[i][k].y);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        if (best == 0.0) return cd_make(0.0, 0.0);
+#pragma unroll
+        for (int i = k + 1; i < C; ++i) {
+            if (i == p) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    cd t = A.a[k][j];
+                    A.a[k][j] = A.a[i][j];
+                    A.a[i][j] = t;
+                }
+                det = cd_make(-det.x, -det.y);
+            }
+        }
+        det = det * A.a[k][k];
+        const cd piv = cd_div(cd_make(1.0, 0.0), A.a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < C; ++i) {
+            const cd f = A.a[i][k] * piv;
+#pragma unroll
+            for (int j = k; j < C; ++j) A.a[i][j] = A.a[i][j] - f * A.a[k][j];
+        }
+    }
+    return det;
+}
+
+// 2-norm condition number by one-sided (Hestenes) Jacobi on the columns: accurate for the small
+// singular values, unlike an eigen-decomposition of A^H A.  Only used in the narrow band where
+// the cheap Frobenius bounds cannot decide the gate.
+template <int C>
+SM_HD double mat_cond2(const Mat<C>& Ain) {
+    Mat<C> A = Ain;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < C - 1; ++p)
+            for (int q = p + 1; q < C; ++q) {
+                double app = 0.0, aqq = 0.0;
+                cd apq = cd_make(0.0, 0.0);
+                for (int i = 0; i < C; ++i) {
+                    app += cd_abs2(A.a[i][p]);
+                    aqq += cd_abs2(A.a[i][q]);
+                    cd_fma(apq, cd_conj(A.a[i][p]), A.a[i][q]);
+                }
+                const double g = cd_abs(apq);
+                if (g == 0.0 || g <= 1e-16 * sqrt(app * aqq)) continue;
+                off = fmax(off, g / sqrt(app * aqq));
+                // rotation that zeroes the (p,q) inner product
+                const cd ph = cd_make(apq.x / g, apq.y / g);      // e^{i arg}
+                const double zeta = (aqq - app) / (2.0 * g);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = 0; i < C; ++i) {
+                    const cd xp = A.a[i][p];
+                    const cd xq = A.a[i][q] * cd_conj(ph);
+                    A.a[i][p] = cd_make(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                    A.a[i][q] = cd_make(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    double smax = 0.0, smin = 1e300;
+    for (int j = 0; j < C; ++j) {
+        double n2 = 0.0;
+        for (int i = 0; i < C; ++i) n2 += cd_abs2(A.a[i][j]);
+        const double s = sqrt(n2);
+        smax = fmax(smax, s);
+        smin = fmin(smin, s);
+    }
+    return smin > 0.0 ? smax / smin : INFINITY;
+}
+
+// Decide `cond_2(A) < threshold` given A and its inverse.  kappa_F = |A|_F |A^-1|_F satisfies
+// kappa_F / C <= cond_2 <= kappa_F, so only C-wide band around the threshold needs the SVD.
+template <int C>
+SM_HD bool cond_below(const Mat<C>& A, const Mat<C>& Ainv, bool invertible, double threshold) {
+    if (!invertible) return false;   // numpy: cond = inf
+    const double kf = sqrt(mat_fro2(A) * mat_fro2(Ainv));
+    if (!(kf == kf)) return false;
+    if (kf < threshold) return true;
+    if (kf >= threshold * C) return false;
+    return mat_cond2(A) < threshold;
+}
+
+// unpack a Hermitian matrix stored as C real diagonals followed by the strictly-lower triangle
+// (row-major pairs (i,j), i > j) as (re, im)
+template <int C>
+SM_HD void herm_unpack(const double* p, Mat<C>& U) {
+    int e = C;
+#pragma unroll
+    for (int i = 0; i < C; ++i) U.a[i][i] = cd_make(p[i], 0.0);
+#pragma unroll
+    for (int i = 1; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            const cd v = cd_make(p[e], p[e + 1]);
+            e += 2;
+            U.a[i][j] = v;
+            U.a[j][i] = cd_conj(v);
+        }
+}
+
+// One iterative-projection row update (src/bss/ilrma.py:516-528; floor_den: src/bss/mnmf.py:883,
+// src/bss/ilrma.py:981).  W row n is replaced in place when the gate passes.
+// use_gate = false follows tILRMA (plain inverse, no condition test, src/bss/ilrma.py:975).
+// Returns 1 (updated), 0 (kept by the gate); *singular is set on an exactly singular W U.
+template <int C>
+SM_HD int ip_row(Mat<C>& W, const Mat<C>& U, int n, double threshold, bool use_gate, bool floor_den, double eps,
+                 bool* singular) {
+    Mat<C> A, Ainv;
+    mat_mul(W, U, A);
+    const bool inv_ok = mat_inverse(A, Ainv);
+    if (!inv_ok) {
+        *singular = true;
+        return 0;
+    }
+    const bool ok = use_gate ? cond_below(A, Ainv, inv_ok, threshold) : true;
+    // w = A^-1 e_n : column n of the inverse (compile-time indexed select)
+    cd w[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        w[i] = Ainv.a[i][0];
+#pragma unroll
+        for (int j = 1; j < C; ++j)
+            if (j == n) w[i] = Ainv.a[i][j];
+    }
+    // q = w^H U w
+    cd q = cd_make(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        cd s = cd_make(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < C; ++j) cd_fma(s, U.a[i][j], w[j]);
+        cd_fma(q, cd_conj(w[i]), s);
+    }
+    cd den = cd_sqrt(q);
+    if (floor_den && cd_less_real(den, eps)) den = cd_make(eps, 0.0);
+    if (ok) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+            if (r == n) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) W.a[r][j] = cd_div(cd_conj(w[j]), den);
+            }
+        }
+    }
+    return ok ? 1 : 0;
+}

@@ -1,0 +1,209 @@
+/*
+ * bssgpu.h -- C ABI of libbssgpu.so, the B200 (sm_100a) implementation of the
+ * STFT-domain blind-source-separation update loop.
+ *
+ * The reference (tky823/audio_source_separation) is pure Python/NumPy and has no FFI of
+ * its own; the boundary it offers is the Python class surface
+ *     Model.__init__ / Model.__call__ / Model.update_once / Model.separate /
+ *     Model.compute_negative_loglikelihood
+ * (src/bss/ilrma.py:183-677, src/bss/iva.py:388-802, src/bss/mnmf.py:637-946,
+ *  src/algorithm/nmf.py:10-595).  Each entry point below names the reference function it
+ * replaces.  All pointers are plain host pointers unless the name says `_device`; arrays use the
+ * reference's own layouts with one extra leading batch axis B (independent mixtures; B = 1
+ * reproduces the reference shapes exactly).  Nothing in this header depends on torch.
+ *
+ * Conventions
+ *   - every function returns BSS_OK (0) or a negative bss_status; bss_last_error() gives text
+ *   - host pointers are borrowed for the duration of the call only
+ *   - a handle is bound to one device and one stream and is not thread-safe
+ *   - dtype arguments select the HOST element type; device storage is complex64/float32 for
+ *     the big tensors and float64 for the per-bin linear algebra (demixing filters, covariances)
+ */
+#ifndef BSSGPU_H
+#define BSSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bss_handle bss_handle;
+
+enum bss_status {
+    BSS_OK = 0,
+    BSS_EINVAL = -1,       /* bad argument / unsupported size (ValueError)              */
+    BSS_ECUDA = -2,        /* CUDA runtime error (RuntimeError)                         */
+    BSS_ESINGULAR = -3,    /* exactly singular bin: np.linalg.LinAlgError in the reference */
+    BSS_ENOMEM = -4,
+    BSS_ESTATE = -5,       /* call order violated (e.g. update before set_input)        */
+    BSS_EUNSUPPORTED = -6  /* NotImplementedError in the reference                      */
+};
+
+enum bss_method {
+    BSS_GAUSS_ILRMA = 0,      /* src/bss/ilrma.py:178  GaussILRMA            */
+    BSS_T_ILRMA = 1,          /* src/bss/ilrma.py:713  tILRMA                */
+    BSS_AUX_LAPLACE_IVA = 2,  /* src/bss/iva.py:388    AuxLaplaceIVA         */
+    BSS_AUX_GAUSS_IVA = 3,    /* src/bss/iva.py:621    AuxGaussIVA           */
+    BSS_FAST_MNMF = 4,        /* src/bss/mnmf.py:637   FastMultichannelISNMF */
+    BSS_NMF_EUC = 10,         /* src/algorithm/nmf.py:150 EUCNMF             */
+    BSS_NMF_KL = 11,          /* src/algorithm/nmf.py:209 KLNMF              */
+    BSS_NMF_IS = 12,          /* src/algorithm/nmf.py:268 ISNMF              */
+    BSS_NMF_T = 13,           /* src/algorithm/nmf.py:358 tNMF               */
+    BSS_NMF_CAUCHY = 14       /* src/algorithm/nmf.py:430 CauchyNMF          */
+};
+
+enum bss_spatial {            /* `algorithm_spatial` of the reference constructors */
+    BSS_SPATIAL_IP = 0,       /* 'IP' / 'IP1'      */
+    BSS_SPATIAL_ISS = 1,      /* 'ISS'             */
+    BSS_SPATIAL_IP2 = 2       /* 'IP2' / 'pairwise' */
+};
+
+enum bss_normalize {
+    BSS_NORMALIZE_NONE = 0,
+    BSS_NORMALIZE_POWER = 1,            /* 'power'            src/bss/ilrma.py:304-322 */
+    BSS_NORMALIZE_PROJECTION_BACK = 2   /* 'projection-back'  src/bss/ilrma.py:323-330 */
+};
+
+enum bss_nmf_algorithm {      /* `algorithm` of the NMF constructors */
+    BSS_ALG_MM = 0,
+    BSS_ALG_ME = 1,
+    BSS_ALG_NAIVE = 2,        /* CauchyNMF 'naive-multipricative' */
+    BSS_ALG_MM_FAST = 3       /* CauchyNMF 'mm_fast'              */
+};
+
+enum bss_dtype { BSS_F32 = 0, BSS_F64 = 1, BSS_C64 = 2, BSS_C128 = 3, BSS_I32 = 4 };
+
+/* State tensors (host layouts, leading B omitted):
+ *   DEMIX_FILTER   (F,N,C) complex   model.demix_filter
+ *   ESTIMATION     (N,F,T) complex   model.estimation
+ *   BASIS          (N,F,K) real      model.basis        ((F,K) when partitioning / NMF)
+ *   ACTIVATION     (N,K,T) real      model.activation   ((K,T) when partitioning / NMF)
+ *   LATENT         (N,K)   real      model.latent       (partitioning only)
+ *   DIAGONALIZER   (F,M,M) complex   FastMNMF model.diagonalizer
+ *   SPATIAL        (N,F,M) real      FastMNMF model.spatial_covariance
+ *   TARGET         (F,T)   real      NMF target
+ *   COVARIANCE     (N,F,C,C) complex weighted covariances of the last spatial update (read only)
+ *   GATE           (N,F)   int32     condition-number gate decisions of the last IP update (read only)
+ */
+enum bss_state {
+    BSS_STATE_DEMIX_FILTER = 0,
+    BSS_STATE_ESTIMATION = 1,
+    BSS_STATE_BASIS = 2,
+    BSS_STATE_ACTIVATION = 3,
+    BSS_STATE_LATENT = 4,
+    BSS_STATE_DIAGONALIZER = 5,
+    BSS_STATE_SPATIAL = 6,
+    BSS_STATE_TARGET = 7,
+    BSS_STATE_COVARIANCE = 8,
+    BSS_STATE_GATE = 9
+};
+
+typedef struct bss_config {
+    int32_t method;        /* enum bss_method                                   */
+    int32_t spatial;       /* enum bss_spatial                                  */
+    int32_t normalize;     /* enum bss_normalize                                */
+    int32_t partitioning;  /* GaussILRMA(partitioning=True)                     */
+    int32_t algorithm;     /* enum bss_nmf_algorithm (NMF family only)          */
+    int32_t n_batch;       /* B independent mixtures (reference: always 1)      */
+    int32_t n_channels;    /* C (FastMNMF: M)                                   */
+    int32_t n_sources;     /* N (== C except FastMNMF)                          */
+    int32_t n_bins;        /* F                                                 */
+    int32_t n_frames;      /* T                                                 */
+    int32_t n_basis;       /* K                                                 */
+    int32_t reference_id;  /* reference microphone of projection back           */
+    int32_t device;        /* CUDA device ordinal                               */
+    int32_t reserved;
+    double domain;         /* 1 <= domain <= 2                                  */
+    double nu;             /* degrees of freedom (tILRMA, tNMF)                 */
+    double eps;            /* EPS = 1e-12        src/bss/ilrma.py:8             */
+    double threshold;      /* THRESHOLD = 1e12   src/bss/ilrma.py:9             */
+} bss_config;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* replaces Model.__init__ + the allocation half of Model._reset (src/bss/ilrma.py:183,50) */
+int bss_create(const bss_config* cfg, bss_handle** out);
+void bss_destroy(bss_handle* h);
+/* text of the last error on this handle (h == NULL: last bss_create failure of this thread) */
+const char* bss_last_error(const bss_handle* h);
+/* run all later work of this handle on `cuda_stream` (a cudaStream_t); NULL = the handle's own stream */
+int bss_set_stream(bss_handle* h, void* cuda_stream);
+int bss_synchronize(bss_handle* h);
+
+/* ---- data in / out ---------------------------------------------------------------------- */
+/* `self.input = input` of Model.__call__ (src/bss/ilrma.py:210): x is (B,C,F,T) complex, host.
+ * Also precomputes the plain spatial covariance mean_t x x^H used by the algebraic forms of
+ * power normalisation and projection back. */
+int bss_set_input(bss_handle* h, const void* x, int dtype);
+/* the state-copy half of Model._reset (src/bss/ilrma.py:67-104) and attribute assignment */
+int bss_set_state(bss_handle* h, int which, const void* src, int dtype);
+/* attribute reads (callbacks, tests) */
+int bss_get_state(bss_handle* h, int which, void* dst, int dtype);
+/* Model._reset defaults that need no host data: W = I (src/bss/ilrma.py:67-69),
+ * FastMNMF Q = I, G = 1e-2 / 1 (src/bss/mnmf.py:660-663), estimation = separate(X, W) */
+int bss_reset_spatial(bss_handle* h);
+
+/* ---- the update loop -------------------------------------------------------------------- */
+/* IP2 pair of the next update (src/bss/ilrma.py:635-646); advanced by the caller exactly as
+ * the reference's __call__ does, not by bss_update_once */
+int bss_set_update_pair(bss_handle* h, int m, int n);
+/* Model.update_once(): src/bss/ilrma.py:286 / :814, src/bss/iva.py:469 / :702,
+ * src/bss/mnmf.py:737, src/algorithm/nmf.py:182,241,302,329,397,461-595 */
+int bss_update_once(bss_handle* h);
+/* n_iter x update_once without returning to the host in between (the `for idx in
+ * range(iteration)` loop of __call__, src/bss/ilrma.py:233, with recordable_loss=False and no
+ * callbacks); advances the IP2 pair schedule itself */
+int bss_run(bss_handle* h, int n_iter);
+/* Model.compute_negative_loglikelihood() (src/bss/ilrma.py:648,993; src/bss/iva.py:604,783;
+ * src/bss/mnmf.py:890) or the NMF criterion (src/algorithm/nmf.py:172-174); loss[B] */
+int bss_loss(bss_handle* h, double* loss);
+/* the tail of Model.__call__ (src/bss/ilrma.py:258-273): Y = separate(X, W), optionally scaled
+ * by projection_back(Y, X[reference_id]) (src/algorithm/projection_back.py:3-34).
+ * y is (B,N,F,T) complex on the host.  FastMNMF: multichannel Wiener filter (src/bss/mnmf.py:919). */
+int bss_separate(bss_handle* h, void* y, int dtype, int apply_projection_back);
+/* same, into a device buffer of complex64 (B,N,F,T) -- used to feed the NCCL gather of a
+ * sharded batch without a host round trip */
+int bss_separate_device(bss_handle* h, void* y_device, int apply_projection_back);
+/* ISS keeps no filter: W = Y X^H (X X^H)^-1 (src/bss/ilrma.py:167-173); result is readable as
+ * BSS_STATE_DEMIX_FILTER afterwards */
+int bss_compute_demix_filter(bss_handle* h);
+
+/* ---- stateless primitives (one launch each; used by the parity tests and ncu) ----------- */
+/* U[n,f] = mean_t x_ft x_ft^H / r[n,f,t]   src/bss/ilrma.py:503-511, src/bss/iva.py:491-499,
+ * src/bss/mnmf.py:875.  x (C,F,T) complex128, r (N,F,T) float64 (already floored),
+ * u (N,F,C,C) complex128. */
+int bss_weighted_covariance(int device, int n_channels, int n_weights, int n_bins, int n_frames,
+                            const void* x, const double* r, void* u);
+/* Gauss-Seidel iterative-projection sweep over all rows   src/bss/ilrma.py:512-530 (floor_den = 0),
+ * src/bss/mnmf.py:872-886 (floor_den = 1).  w (F,N,C) complex128 in/out, u (N,F,C,C) complex128,
+ * gate (N,F) int32 out (may be NULL). */
+int bss_ip_update(int device, int n_channels, int n_bins, void* w, const void* u, int32_t* gate,
+                  double threshold, int floor_den, double eps);
+/* scale (N,F) complex128 = projection_back(Y = W X, X[reference_id]) computed from W and the
+ * plain covariance of x   src/algorithm/projection_back.py:12-21 */
+int bss_projection_back_scale(int device, int n_channels, int n_bins, int n_frames, const void* x,
+                              const void* w, int reference_id, void* scale);
+
+/* Model.separate(input, demix_filter)   src/bss/ilrma.py:153-165, src/bss/iva.py:105-117.
+ * x (C,F,T) complex128, w (F,C,C) complex128, y (C,F,T) complex128; `flags` is reserved (0). */
+int bss_demix(int device, int n_channels, int n_bins, int n_frames, int flags, const void* x, const void* w,
+              void* y);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* CUDA-event timing on the handle's stream: begin/end bracket a region, elapsed in ms */
+int bss_timer_begin(bss_handle* h);
+int bss_timer_end(bss_handle* h, float* elapsed_ms);
+/* time `repeat` launches of the covariance-accumulate kernel alone on the current state;
+ * returns the mean launch duration in ms (CUDA events on the handle's stream) */
+int bss_time_covariance(bss_handle* h, int repeat, float* mean_ms);
+/* number of kernel launches issued by this handle so far */
+int64_t bss_launch_count(const bss_handle* h);
+/* raw device buffers for zero-copy interop (documented layouts) */
+int bss_device_buffer(bss_handle* h, int which, void** dptr, size_t* bytes);
+const char* bss_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSSGPU_H */

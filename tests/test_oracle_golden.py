@@ -1,0 +1,99 @@
+"""CPU: the oracle restatement reproduces every fixture generated from the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel
+from oracle import core, ilrma, auxiva, fastmnmf, nmf
+
+TOL = 1e-9
+
+ILRMA_CASES = ['ilrma_ip_power_d2', 'ilrma_ip_power_d1', 'ilrma_ip_pb_d2', 'ilrma_iss_power_d2', 'ilrma_iss_pb_d1',
+               'ilrma_ip2_power_d2', 'ilrma_ip2_power_c2', 'ilrma_ip_power_part']
+AUXIVA_CASES = ['auxiva_laplace_ip', 'auxiva_laplace_ip_c4', 'auxiva_gauss_ip', 'auxiva_laplace_iss', 'auxiva_gauss_iss',
+                'auxiva_laplace_ip2']
+NMF_CASES = ['nmf_euc_d2', 'nmf_euc_d1', 'nmf_kl_d2', 'nmf_kl_d1', 'nmf_is_mm_d2', 'nmf_is_mm_d1', 'nmf_is_me', 'nmf_t',
+             'nmf_cauchy_naive_multipricative', 'nmf_cauchy_mm', 'nmf_cauchy_me', 'nmf_cauchy_mm_fast']
+
+
+@pytest.mark.parametrize('name', ILRMA_CASES)
+def test_ilrma(name):
+    meta, i, o = load_golden(name)
+    presets = {'W': i['W0'], 'T': i['T0'], 'V': i['V0']}
+    if meta['partitioning']:
+        presets['Z'] = i['Z0']
+    out, st, loss = ilrma.run(i['X'], iteration=meta['iteration'], n_basis=meta['n_basis'], spatial=meta['algorithm_spatial'],
+                              domain=meta['domain'], normalize_mode=meta['normalize'], partitioning=meta['partitioning'], **presets)
+    tol = 1e-7 if meta['algorithm_spatial'] in ('IP2', 'pairwise') else TOL
+    assert rel(out, o['output']) < tol
+    assert rel(st['T'], o['basis']) < tol
+    assert rel(st['V'], o['activation']) < tol
+    assert rel(loss, o['loss']) < tol
+    W = st['W'] if st['W'] is not None else st['W_final']
+    assert rel(W, o['demix_filter']) < tol
+
+
+def test_ilrma_seeded_dropin():
+    meta, i, o = load_golden('ilrma_seeded_dropin')
+    np.random.seed(meta['seed'])
+    out, st, loss = ilrma.run(i['X'], iteration=meta['iteration'], n_basis=meta['n_basis'])
+    assert rel(out, o['output']) < TOL and rel(loss, o['loss']) < TOL
+
+
+def test_tilrma():
+    meta, i, o = load_golden('tilrma_nu5')
+    out, st, loss = ilrma.t_run(i['X'], iteration=meta['iteration'], n_basis=meta['n_basis'], nu=meta['nu'], W=i['W0'], T=i['T0'],
+                                V=i['V0'])
+    assert rel(out, o['output']) < TOL and rel(loss, o['loss']) < TOL and rel(st['W'], o['demix_filter']) < TOL
+
+
+@pytest.mark.parametrize('name', AUXIVA_CASES)
+def test_auxiva(name):
+    meta, i, o = load_golden(name)
+    kind = 'laplace' if meta['model'] == 'AuxLaplaceIVA' else 'gauss'
+    out, st, loss = auxiva.run(i['X'], iteration=meta['iteration'], kind=kind, spatial=meta['algorithm_spatial'], W=i['W0'])
+    tol = 1e-7 if meta['algorithm_spatial'] in ('IP2', 'pairwise') else TOL
+    assert rel(out, o['output']) < tol and rel(loss, o['loss']) < tol
+
+
+@pytest.mark.parametrize('name', ['fastmnmf_m3n3', 'fastmnmf_m4n2'])
+def test_fastmnmf(name):
+    meta, i, o = load_golden(name)
+    out, st, loss = fastmnmf.run(i['X'], iteration=meta['iteration'], n_basis=meta['n_basis'], n_sources=meta['n_sources'],
+                                 W=i['W0'], H=i['H0'])
+    assert rel(out, o['output']) < TOL and rel(loss, o['loss']) < TOL
+    assert rel(st['Q'], o['diagonalizer']) < TOL and rel(st['G'], o['spatial_covariance']) < TOL
+
+
+@pytest.mark.parametrize('name', NMF_CASES)
+def test_nmf(name):
+    meta, i, o = load_golden(name)
+    T, V, loss = nmf.run(meta['model'], i['Z'], n_basis=meta['n_basis'], iteration=meta['iteration'], domain=meta['domain'],
+                         algorithm=meta['algorithm'], nu=meta['nu'], T=i['T0'], V=i['V0'])
+    assert rel(T, o['basis']) < TOL and rel(V, o['activation']) < TOL and rel(loss, o['loss']) < TOL
+
+
+def test_primitives():
+    meta, i, o = load_golden('primitives')
+    assert rel(core.weighted_covariance(i['X'], i['R']), o['U']) < 1e-13
+    Y = core.demix(i['X'], i['W'])
+    assert rel(core.projection_back_scale(Y, i['X'][0]), o['scale2']) < 1e-13
+    assert rel(core.projection_back_scale(Y, i['X']), o['scale3']) < 1e-13
+    order = np.argsort(i['eigval'], axis=-1)[:, ::-1]
+    assert np.array_equal(order, o['order'])
+    assert np.array_equal(core.gather_by_order(i['eigvec'].swapaxes(-2, -1), order, axis=-2), o['sorted'])
+    for n_src in (2, 3, 4):
+        pair, seq = None, []
+        for _ in range(7):
+            pair = core.next_update_pair(pair, n_src)
+            seq.append(pair)
+        assert np.array_equal(np.array(seq), o['pairs{}'.format(n_src)])
+
+
+def test_known_answer_losses():
+    """first loss values of the reference on mix2(4,513,128), K=2 (unrounded initial state)."""
+    from oracle import synth
+    X = synth.mix2(4, 513, 128, seed=0)
+    W0, T0, V0 = synth.initial_state(4, 513, 128, 2, seed=7, round32=False)
+    _, _, loss = ilrma.run(X, iteration=2, n_basis=2, W=W0, T=T0, V=V0)
+    want = [7.2776542359e5, 4.3845892818e4, 2.8737622949e4]
+    assert np.allclose(loss, want, rtol=1e-9)
