@@ -21,6 +21,12 @@ __device__ __forceinline__ void cf_fma(cf& acc, cf a, cf b) {
     acc.y = fmaf(a.y, b.x, acc.y);
 }
 
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ------------------------------------------------------------------------------ mbarrier / bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -221,18 +227,18 @@ struct WarpStream {
 // host-side geometry of a [rows][Tp] bin tile: whole when small, 256-frame slabs otherwise
 #define BSS_SLAB_FRAMES 256
 #define BSS_WHOLE_TILE_BYTES 8192
-static inline TileGeom make_tile_geom(int rows, int Tp) {
+static inline TileGeom make_tile_geom(int rows, int Tp, int slab_frames = BSS_SLAB_FRAMES) {
     TileGeom g;
     g.n_rows = rows;
     g.row_len = Tp;
-    if ((size_t)rows * Tp * 8 <= BSS_WHOLE_TILE_BYTES) {
+    if (Tp <= slab_frames) {
         g.slab = Tp;
         g.n_slabs = 1;
         g.row_stride = Tp;
     } else {
-        g.slab = BSS_SLAB_FRAMES;
-        g.n_slabs = (Tp + BSS_SLAB_FRAMES - 1) / BSS_SLAB_FRAMES;
-        g.row_stride = BSS_SLAB_FRAMES;
+        g.slab = slab_frames;
+        g.n_slabs = (Tp + slab_frames - 1) / slab_frames;
+        g.row_stride = slab_frames;
     }
     g.stage_bytes = (uint32_t)(((size_t)rows * g.row_stride * 8 + 127) / 128 * 128);
     return g;

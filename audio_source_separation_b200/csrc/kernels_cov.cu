@@ -3,16 +3,20 @@
 //
 // One warp owns one (mixture, bin, weight-group) item at a time.  Lane 0 streams the bin's
 // C x Tp complex64 tile from HBM into the warp's private shared-memory ring with bulk async
-// copies (TMA engine) signalled through mbarriers; the 32 lanes then walk the frames two at a
-// time (one conflict-free LDS.128 per channel), recompute the weights from the low-rank source
-// model in registers, accumulate the packed Hermitian outer products in fp32 registers and
-// finish with a butterfly reduce-scatter over the lanes.  Nothing of size (N,F,T,C,C) -- the
-// tensor the reference materialises -- ever exists.
+// copies (TMA engine, UBLKCP) signalled through mbarriers; the 32 lanes then walk the frames two
+// at a time (one conflict-free LDS.128 per channel), recompute the weights from the low-rank
+// source model in registers, and accumulate the packed Hermitian outer products with paired
+// fp32 FMAs (FFMA2: one instruction updates the (re, im) pair of an entry; the weight and the
+// swapped/negated operand come for free as operand modifiers).  A butterfly reduce-scatter over
+// the lanes finishes the bin.  Nothing of size (N,F,T,C,C) -- the tensor the reference
+// materialises -- ever exists.
 #include "handle.h"
 
 namespace {
 
 constexpr int COV_STAGES = 3;
+constexpr int COV_SLAB = 128;   // frames per ring stage
+constexpr int COV_MAX_WARPS = 16;
 
 struct CovParams {
     CovArgs a;
@@ -23,42 +27,56 @@ struct CovParams {
     uint32_t scratch_off, scratch_stride, ring_off;
 };
 
+// Pair layout of one Hermitian accumulator: DP = ceil(C/2) diagonal pairs (d0,d1), (d2,d3), ...
+// followed by the strictly-lower entries (i > j, row major) as (re, im).
+template <int C>
+struct Pairs {
+    static constexpr int DP = (C + 1) / 2;
+    static constexpr int NP = DP + C * (C - 1) / 2;
+};
+
 template <int C, int NS>
-__device__ __forceinline__ void accumulate_frame(float* acc, const cf* x, const float* w) {
-    constexpr int CC = C * C;
+__device__ __forceinline__ void accumulate_frame(float2 (&acc)[NS][Pairs<C>::NP], const float2 (&x)[C], const float (&w)[NS]) {
+    constexpr int DP = Pairs<C>::DP;
+    float2 v[Pairs<C>::NP];
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-        const float d = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) acc[s * CC + i] = fmaf(w[s], d, acc[s * CC + i]);
+    for (int i = 0; i < DP; ++i) {
+        const float d0 = fmaf(x[2 * i].x, x[2 * i].x, x[2 * i].y * x[2 * i].y);
+        float d1 = 0.f;
+        if (2 * i + 1 < C) d1 = fmaf(x[2 * i + 1].x, x[2 * i + 1].x, x[2 * i + 1].y * x[2 * i + 1].y);
+        v[i] = make_float2(d0, d1);
     }
-    int e = C;
+    int e = DP;
 #pragma unroll
     for (int i = 1; i < C; ++i)
 #pragma unroll
         for (int j = 0; j < i; ++j) {
-            // x_i conj(x_j)
-            const float re = fmaf(x[i].x, x[j].x, x[i].y * x[j].y);
-            const float im = fmaf(x[i].y, x[j].x, -x[i].x * x[j].y);
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                acc[s * CC + e] = fmaf(w[s], re, acc[s * CC + e]);
-                acc[s * CC + e + 1] = fmaf(w[s], im, acc[s * CC + e + 1]);
-            }
-            e += 2;
+            // x_i conj(x_j) = x_i * x_j.x + (x_i.y, -x_i.x) * x_j.y
+            const float2 t = __fmul2_rn(x[i], make_float2(x[j].x, x[j].x));
+            v[e] = __ffma2_rn(make_float2(x[i].y, -x[i].x), make_float2(x[j].y, x[j].y), t);
+            ++e;
         }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const float2 ww = make_float2(w[s], w[s]);
+#pragma unroll
+        for (int q = 0; q < Pairs<C>::NP; ++q) acc[s][q] = __ffma2_rn(v[q], ww, acc[s][q]);
+    }
 }
 
-template <int C, int NS, int WM>
-__global__ void __launch_bounds__(256) cov_kernel(const CovParams p) {
+// KT > 0: n_basis known at compile time (basis row in registers); KT == 0: run-time K, basis row in smem.
+template <int C, int NS, int WM, int KT, bool POW>
+__global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     const CovArgs& a = p.a;
-    constexpr int CC = C * C;
-    constexpr int M = NS * CC;
+    constexpr int NP = Pairs<C>::NP;
+    constexpr int DP = Pairs<C>::DP;
+    constexpr int M = NS * NP * 2;
     constexpr int MP = (M + 31) / 32 * 32;
     constexpr int Q = MP / 32;
+    constexpr int CC = C * C;
 
     float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);
     WarpStream<COV_STAGES> st;
@@ -66,37 +84,59 @@ __global__ void __launch_bounds__(256) cov_kernel(const CovParams p) {
              smem + p.ring_off + (size_t)warp * COV_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
              (long long)gridDim.x * wpc, p.n_items, p.n_groups, lane);
     const int row_stride = p.g.row_stride;
+    const int Tp = a.Tp;
+    const int K = KT > 0 ? KT : a.K;
 
-    float acc[MP];
+    float2 acc[NS][NP];
 #pragma unroll
-    for (int i = 0; i < MP; ++i) acc[i] = 0.f;
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[s][q] = make_float2(0.f, 0.f);
+
+    // per-item state
+    int b = 0, f = 0, w0 = 0;
+    const float* wrow[NS];          // per weight set: activation rows / frame weights / explicit weights of this item
+    float tbr[NS][KT > 0 ? KT : 1];
+    bool live[NS];
 
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
-        const long long bf = st.cons.item / p.n_groups;
-        const int grp = (int)(st.cons.item - bf * p.n_groups);
-        const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
-        const int w0 = grp * NS;
-
-        int src[NS];
+        if (st.first_slab()) {
+            const long long bf = st.cons.item / p.n_groups;
+            const int grp = (int)(st.cons.item - bf * p.n_groups);
+            b = (int)(bf / a.F);
+            f = (int)(bf - (long long)b * a.F);
+            w0 = grp * NS;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) src[s] = (w0 + s < a.n_sel) ? a.wsel[w0 + s] : -1;
-
-        if (WM == WM_ILRMA && st.first_slab()) {
-            for (int i = lane; i < NS * a.K; i += 32) {
-                const int s = i / a.K, k = i - s * a.K;
-                const int sw = (w0 + s < a.n_sel) ? a.wsel[w0 + s] : 0;
-                tb[i] = a.basis[(((size_t)b * a.NW + sw) * a.F + f) * a.K + k];
+            for (int s = 0; s < NS; ++s) {
+                live[s] = w0 + s < a.n_sel;
+                const int sw = live[s] ? a.wsel[w0 + s] : 0;
+                if (WM == WM_ILRMA) {
+                    wrow[s] = a.act + ((size_t)b * a.NW + sw) * K * Tp;
+                    const float* tsrc = a.basis + (((size_t)b * a.NW + sw) * a.F + f) * K;
+                    if (KT > 0) {
+#pragma unroll
+                        for (int k = 0; k < (KT > 0 ? KT : 1); ++k) tbr[s][k] = __ldg(tsrc + k);
+                    } else {
+                        for (int k = lane; k < K; k += 32) tb[s * K + k] = __ldg(tsrc + k);
+                    }
+                } else if (WM == WM_FRAME) {
+                    wrow[s] = a.wfr + ((size_t)b * a.NW + sw) * Tp;
+                } else if (WM == WM_EXPLICIT) {
+                    wrow[s] = a.iw + (((size_t)b * a.F + f) * a.NW + sw) * Tp;
+                } else {
+                    wrow[s] = nullptr;
+                }
             }
-            __syncwarp();
+            if (WM == WM_ILRMA && KT == 0) __syncwarp();
         }
 
         const cf* xs = st.acquire();
         const int nf = st.frames();
         const int tbase = st.frame0();
 
-#pragma unroll 1
+#pragma unroll 2
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
@@ -106,88 +146,102 @@ __global__ void __launch_bounds__(256) cov_kernel(const CovParams p) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 if (WM == WM_UNIT) {
-                    wa[s] = wb[s] = (src[s] >= 0) ? 1.f : 0.f;
-                } else if (src[s] < 0) {
-                    wa[s] = wb[s] = 0.f;
+                    wa[s] = wb[s] = live[s] ? 1.f : 0.f;
                 } else if (WM == WM_ILRMA) {
-                    const float* v = a.act + ((size_t)b * a.NW + src[s]) * a.K * a.Tp + t;
-                    float ra = 0.f, rb = 0.f;
-                    for (int k = 0; k < a.K; ++k) {
-                        const float2 vv = __ldg(reinterpret_cast<const float2*>(v + (size_t)k * a.Tp));
-                        const float tk = tb[s * a.K + k];
-                        ra = fmaf(tk, vv.x, ra);
-                        rb = fmaf(tk, vv.y, rb);
+                    float2 r = make_float2(0.f, 0.f);
+                    if (KT > 0) {
+#pragma unroll
+                        for (int k = 0; k < (KT > 0 ? KT : 1); ++k) {
+                            const float2 vv = __ldg(reinterpret_cast<const float2*>(wrow[s] + (size_t)k * Tp + t));
+                            r = __ffma2_rn(vv, make_float2(tbr[s][k], tbr[s][k]), r);
+                        }
+                    } else {
+                        for (int k = 0; k < K; ++k) {
+                            const float2 vv = __ldg(reinterpret_cast<const float2*>(wrow[s] + (size_t)k * Tp + t));
+                            const float tk = tb[s * K + k];
+                            r = __ffma2_rn(vv, make_float2(tk, tk), r);
+                        }
                     }
-                    if (a.expo != 1.f) {
-                        ra = powf(ra, a.expo);
-                        rb = powf(rb, a.expo);
+                    if (POW) {
+                        r.x = powf(r.x, a.expo);
+                        r.y = powf(r.y, a.expo);
                     }
-                    ra = ra < a.eps ? a.eps : ra;
-                    rb = rb < a.eps ? a.eps : rb;
-                    wa[s] = __frcp_rn(ra);
-                    wb[s] = __frcp_rn(rb);
-                } else if (WM == WM_FRAME) {
-                    const float2 vv =
-                        __ldg(reinterpret_cast<const float2*>(a.wfr + ((size_t)b * a.NW + src[s]) * a.Tp + t));
-                    wa[s] = vv.x;
-                    wb[s] = vv.y;
+                    r.x = fmaxf(r.x, a.eps);
+                    r.y = fmaxf(r.y, a.eps);
+                    wa[s] = live[s] ? rcp_fast(r.x) : 0.f;
+                    wb[s] = live[s] ? rcp_fast(r.y) : 0.f;
                 } else {
-                    const float2 vv = __ldg(reinterpret_cast<const float2*>(
-                        a.iw + (((size_t)b * a.F + f) * a.NW + src[s]) * a.Tp + t));
-                    wa[s] = vv.x;
-                    wb[s] = vv.y;
+                    const float2 vv = __ldg(reinterpret_cast<const float2*>(wrow[s] + t));
+                    wa[s] = live[s] ? vv.x : 0.f;
+                    wb[s] = live[s] ? vv.y : 0.f;
                 }
             }
-            cf x0[C], x1[C];
+            float2 x0[C], x1[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                x0[c] = cf_make(xv[c].x, xv[c].y);
-                x1[c] = cf_make(xv[c].z, xv[c].w);
+                x0[c] = make_float2(xv[c].x, xv[c].y);
+                x1[c] = make_float2(xv[c].z, xv[c].w);
             }
             accumulate_frame<C, NS>(acc, x0, wa);
             accumulate_frame<C, NS>(acc, x1, wb);
         }
 
         if (st.last_slab()) {
-            warp_reduce_scatter<MP>(acc, lane);
+            float flat[MP];
+#pragma unroll
+            for (int i = 0; i < MP; ++i) flat[i] = 0.f;
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    flat[(s * NP + q) * 2] = acc[s][q].x;
+                    flat[(s * NP + q) * 2 + 1] = acc[s][q].y;
+                    acc[s][q] = make_float2(0.f, 0.f);
+                }
+            warp_reduce_scatter<MP>(flat, lane);
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int e = Q * lane + q;
-                const int s = e / CC, r = e - s * CC;
-                if (s < NS && w0 + s < a.n_sel) {
+                const int s = e / (2 * NP);
+                int r = e - s * 2 * NP;   // float index inside the pair layout
+                // pair layout -> packed output layout (C diagonal reals, then lower (re, im) pairs)
+                bool valid = s < NS && w0 + s < a.n_sel;
+                if (r >= 2 * DP)
+                    r = r - 2 * DP + C;
+                else if (r >= C)
+                    valid = false;   // padding slot of an odd C
+                if (valid) {
                     const int sw = a.wsel[w0 + s];
-                    a.U[(((size_t)b * a.NW + sw) * a.F + f) * CC + r] = (double)acc[q] * p.inv_T;
+                    a.U[(((size_t)b * a.NW + sw) * a.F + f) * CC + r] = (double)flat[q] * p.inv_T;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < MP; ++i) acc[i] = 0.f;
         }
         st.release();
     }
 }
 
-template <int C, int NS, int WM>
+template <int C, int NS, int WM, int KT, bool POW>
 int launch_cov_t(bss_handle* h, const CovArgs& a) {
     CovParams p;
     p.a = a;
-    p.g = make_tile_geom(C, a.Tp);
+    p.g = make_tile_geom(C, a.Tp, COV_SLAB);
     p.n_groups = (a.n_sel + NS - 1) / NS;
     p.n_items = (long long)a.B * a.F * p.n_groups;
     p.inv_T = 1.0 / (double)a.T;
     if (p.n_items == 0) return BSS_OK;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, COV_STAGES, (size_t)NS * (a.K > 0 ? a.K : 1) * 4, p.n_items, 8, &sp))
+    if (!plan_stream(h, p.g, COV_STAGES, (size_t)NS * (a.K > 0 ? a.K : 1) * 4, p.n_items, COV_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "covariance: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
     p.ring_off = sp.ring_off;
     static bool attr_done = false;
     if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(cov_kernel<C, NS, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BSS_CUDA(h, cudaFuncSetAttribute(cov_kernel<C, NS, WM, KT, POW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          h->max_smem));
         attr_done = true;
     }
-    cov_kernel<C, NS, WM><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
+    cov_kernel<C, NS, WM, KT, POW><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
@@ -196,10 +250,13 @@ int launch_cov_t(bss_handle* h, const CovArgs& a) {
 template <int C, int NS>
 int launch_cov_wm(bss_handle* h, const CovArgs& a) {
     switch (a.wmode) {
-        case WM_UNIT: return launch_cov_t<C, NS, WM_UNIT>(h, a);
-        case WM_ILRMA: return launch_cov_t<C, NS, WM_ILRMA>(h, a);
-        case WM_FRAME: return launch_cov_t<C, NS, WM_FRAME>(h, a);
-        case WM_EXPLICIT: return launch_cov_t<C, NS, WM_EXPLICIT>(h, a);
+        case WM_UNIT: return launch_cov_t<C, NS, WM_UNIT, 1, false>(h, a);
+        case WM_ILRMA:
+            if (a.expo != 1.f) return launch_cov_t<C, NS, WM_ILRMA, 0, true>(h, a);
+            if (a.K == 2) return launch_cov_t<C, NS, WM_ILRMA, 2, false>(h, a);
+            return launch_cov_t<C, NS, WM_ILRMA, 0, false>(h, a);
+        case WM_FRAME: return launch_cov_t<C, NS, WM_FRAME, 1, false>(h, a);
+        case WM_EXPLICIT: return launch_cov_t<C, NS, WM_EXPLICIT, 1, false>(h, a);
     }
     return bss_fail(h, BSS_EINVAL, "covariance: unknown weight mode");
 }

@@ -12,25 +12,6 @@ namespace {
 
 constexpr int MU_STAGES = 3;
 
-// a = dL/d(1/TV)-like numerator statistic, b = 1/TV   (TV already floored)
-__device__ __forceinline__ void mu_stats(int mode, float P, float tv, float p_exp, float nu, float& a, float& b) {
-    b = __frcp_rn(tv);
-    if (mode == 0) {
-        // Gauss / IS:  P / TV^p
-        if (p_exp == 2.f)
-            a = P * b * b;
-        else
-            a = P / powf(tv, p_exp);
-    } else {
-        // Student-t: h / TV^2,  h = 1 / (2/((2+nu) TV) + nu/((2+nu) P))    src/bss/ilrma.py:922
-        const float c = 2.f + nu;
-        const float h = 1.f / (2.f / (c * tv) + nu / (c * P));
-        a = h * b * b;
-    }
-}
-
-__device__ __forceinline__ float pow_q(float r, float q) { return q == 0.5f ? sqrtf(r) : powf(r, q); }
-
 template <int C, bool FROM_Y>
 __device__ __forceinline__ void load_filter(cf (&w)[C][C], const cf* Wf) {
     if (!FROM_Y) {
@@ -60,316 +41,6 @@ __device__ __forceinline__ void frame_power(const float4 (&xv)[C], const cf (&w)
             P1[n] = cf_abs2(y1);
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------- basis
-struct MuParams {
-    MuArgs a;
-    TileGeom g;
-    long long n_items;
-    int n_kc;
-    uint32_t scratch_off, scratch_stride, ring_off;
-};
-
-template <int C, int KC, bool FROM_Y>
-__global__ void __launch_bounds__(256) mu_basis_kernel(const MuParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = blockDim.x >> 5;
-    const MuArgs& a = p.a;
-    constexpr int N = C;
-    constexpr int M = N * KC * 2;
-    constexpr int MP = (M + 31) / 32 * 32;
-    constexpr int Q = MP / 32;
-    const int K = a.K;
-
-    float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);   // [N][K]
-    float* red = tb + N * K;                                                                        // [MP]
-    WarpStream<MU_STAGES> st;
-    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
-             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
-             (long long)blockIdx.x * wpc + warp, (long long)gridDim.x * wpc, p.n_items, p.n_kc, lane);
-    const int row_stride = p.g.row_stride;
-
-    float acc[MP];
-#pragma unroll
-    for (int i = 0; i < MP; ++i) acc[i] = 0.f;
-    cf w[C][C];
-
-#pragma unroll 1
-    while (st.active()) {
-        st.issue_next();
-        const long long bf = st.cons.item / p.n_kc;
-        const int kc = (int)(st.cons.item - bf * p.n_kc);
-        const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
-        const int k0 = kc * KC;
-
-        if (st.first_slab()) {
-            for (int i = lane; i < N * K; i += 32) {
-                const int n = i / K, k = i - n * K;
-                tb[i] = a.basis[(((size_t)b * N + n) * a.F + f) * K + k];
-            }
-            load_filter<C, FROM_Y>(w, a.Wf + (size_t)bf * C * C);
-            __syncwarp();
-        }
-
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
-#pragma unroll 1
-        for (int tt = 2 * lane; tt < nf; tt += 64) {
-            float4 xv[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
-            float P0[C], P1[C];
-            frame_power<C, FROM_Y>(xv, w, P0, P1);
-            const int t = tbase + tt;
-#pragma unroll
-            for (int n = 0; n < N; ++n) {
-                const float* v = a.act + ((size_t)b * N + n) * K * a.Tp + t;
-                float tv0 = 0.f, tv1 = 0.f;
-                float2 vk[KC];
-#pragma unroll
-                for (int kk = 0; kk < KC; ++kk) vk[kk] = make_float2(0.f, 0.f);
-                for (int k = 0; k < K; ++k) {
-                    const float2 vv = __ldg(reinterpret_cast<const float2*>(v + (size_t)k * a.Tp));
-                    const float tk = tb[n * K + k];
-                    tv0 = fmaf(tk, vv.x, tv0);
-                    tv1 = fmaf(tk, vv.y, tv1);
-#pragma unroll
-                    for (int kk = 0; kk < KC; ++kk)
-                        if (k == k0 + kk) vk[kk] = vv;
-                }
-                tv0 = tv0 < a.eps ? a.eps : tv0;
-                tv1 = tv1 < a.eps ? a.eps : tv1;
-                float a0, b0, a1, b1;
-                mu_stats(a.mode, P0[n], tv0, a.p_exp, a.nu, a0, b0);
-                mu_stats(a.mode, P1[n], tv1, a.p_exp, a.nu, a1, b1);
-#pragma unroll
-                for (int kk = 0; kk < KC; ++kk) {
-                    float& num = acc[(n * KC + kk) * 2];
-                    float& den = acc[(n * KC + kk) * 2 + 1];
-                    num = fmaf(a0, vk[kk].x, num);
-                    num = fmaf(a1, vk[kk].y, num);
-                    den = fmaf(b0, vk[kk].x, den);
-                    den = fmaf(b1, vk[kk].y, den);
-                }
-            }
-        }
-
-        if (st.last_slab()) {
-            warp_reduce_scatter<MP>(acc, lane);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) red[Q * lane + q] = acc[q];
-            __syncwarp();
-            for (int i = lane; i < N * KC; i += 32) {
-                const int n = i / KC, kk = i - n * KC, k = k0 + kk;
-                if (k < K) {
-                    const float num = red[2 * i];
-                    float den = red[2 * i + 1];
-                    den = den < a.eps ? a.eps : den;
-                    const float told = tb[n * K + k];
-                    const bool sel = a.sel_m < 0 || n == a.sel_m || n == a.sel_n;
-                    a.basis_out[(((size_t)b * N + n) * a.F + f) * K + k] = sel ? told * pow_q(num / den, a.q_exp) : told;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < MP; ++i) acc[i] = 0.f;
-        }
-        st.release();
-    }
-}
-
-template <int C, int KC, bool FROM_Y>
-int launch_mu_basis_t(bss_handle* h, const MuArgs& a) {
-    MuParams p;
-    p.a = a;
-    p.g = make_tile_geom(C, a.Tp);
-    p.n_kc = (a.K + KC - 1) / KC;
-    p.n_items = (long long)a.B * a.F * p.n_kc;
-    constexpr int MP = (C * KC * 2 + 31) / 32 * 32;
-    StreamPlan sp;
-    if (!plan_stream(h, p.g, MU_STAGES, ((size_t)C * a.K + MP) * 4, p.n_items, 8, &sp))
-        return bss_fail(h, BSS_EINVAL, "source model: frame tile does not fit in shared memory");
-    p.scratch_off = sp.scratch_off;
-    p.scratch_stride = sp.scratch_stride;
-    p.ring_off = sp.ring_off;
-    static bool attr_done = false;
-    if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         h->max_smem));
-        attr_done = true;
-    }
-    mu_basis_kernel<C, KC, FROM_Y><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
-    h->launches++;
-    BSS_CUDA(h, cudaGetLastError());
-    return BSS_OK;
-}
-
-// ------------------------------------------------------------------------------------------- activation
-// Stage 1: a warp owns 64 frames (two per lane) of one mixture and walks a chunk of bins, reading
-// the 512-byte row segments straight from global memory; partial sums go to `part`.
-// part layout: [B][n_chunks][N][K][2][Tp]
-template <int C, int KC, bool FROM_Y>
-__global__ void __launch_bounds__(128) mu_act_partial_kernel(const MuArgs a, float* part, int n_chunks, int bins_per_chunk,
-                                                            int n_slabs, int n_kc, long long n_items) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = blockDim.x >> 5;
-    const long long item = (long long)blockIdx.x * wpc + warp;
-    if (item >= n_items) return;
-    constexpr int N = C;
-    const int K = a.K;
-    // item -> (b, chunk, slab, kc), kc fastest so that the k-chunks of a tile run side by side
-    long long r = item;
-    const int kc = (int)(r % n_kc);
-    r /= n_kc;
-    const int slab = (int)(r % n_slabs);
-    r /= n_slabs;
-    const int chunk = (int)(r % n_chunks);
-    const int b = (int)(r / n_chunks);
-    const int k0 = kc * KC;
-    const int t0 = slab * 64 + 2 * lane;
-    const bool live = t0 < a.Tp;
-
-    // activation slab of this warp: vs[n][k][64]
-    float* vs = reinterpret_cast<float*>(smem) + (size_t)warp * N * K * 64;
-    for (int i = 0; i < N * K; ++i) {
-        float2 vv = make_float2(0.f, 0.f);
-        if (live) vv = __ldg(reinterpret_cast<const float2*>(a.act + ((size_t)b * N * K + i) * a.Tp + t0));
-        *reinterpret_cast<float2*>(vs + (size_t)i * 64 + 2 * lane) = vv;
-    }
-    __syncwarp();
-
-    float num0[N][KC], num1[N][KC], den0[N][KC], den1[N][KC];
-#pragma unroll
-    for (int n = 0; n < N; ++n)
-#pragma unroll
-        for (int kk = 0; kk < KC; ++kk) num0[n][kk] = num1[n][kk] = den0[n][kk] = den1[n][kk] = 0.f;
-
-    const int f_begin = chunk * bins_per_chunk;
-    const int f_end = min(a.F, f_begin + bins_per_chunk);
-    const cf* src = FROM_Y ? a.Y : a.X;
-#pragma unroll 1
-    for (int f = f_begin; f < f_end; ++f) {
-        const size_t bf = (size_t)b * a.F + f;
-        float4 xv[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(src + (bf * C + c) * a.Tp + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        cf w[C][C];
-        load_filter<C, FROM_Y>(w, a.Wf + bf * C * C);
-        float P0[C], P1[C];
-        frame_power<C, FROM_Y>(xv, w, P0, P1);
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-            const float* tbn = a.basis + ((size_t)b * N + n) * a.F * K + (size_t)f * K;
-            float tv0 = 0.f, tv1 = 0.f;
-            float tk[KC];
-#pragma unroll
-            for (int kk = 0; kk < KC; ++kk) tk[kk] = 0.f;
-            for (int k = 0; k < K; ++k) {
-                const float tkv = __ldg(tbn + k);
-                const float2 vv = *reinterpret_cast<const float2*>(vs + ((size_t)n * K + k) * 64 + 2 * lane);
-                tv0 = fmaf(tkv, vv.x, tv0);
-                tv1 = fmaf(tkv, vv.y, tv1);
-#pragma unroll
-                for (int kk = 0; kk < KC; ++kk)
-                    if (k == k0 + kk) tk[kk] = tkv;
-            }
-            tv0 = tv0 < a.eps ? a.eps : tv0;
-            tv1 = tv1 < a.eps ? a.eps : tv1;
-            float a0, b0, a1, b1;
-            mu_stats(a.mode, P0[n], tv0, a.p_exp, a.nu, a0, b0);
-            mu_stats(a.mode, P1[n], tv1, a.p_exp, a.nu, a1, b1);
-#pragma unroll
-            for (int kk = 0; kk < KC; ++kk) {
-                num0[n][kk] = fmaf(tk[kk], a0, num0[n][kk]);
-                num1[n][kk] = fmaf(tk[kk], a1, num1[n][kk]);
-                den0[n][kk] = fmaf(tk[kk], b0, den0[n][kk]);
-                den1[n][kk] = fmaf(tk[kk], b1, den1[n][kk]);
-            }
-        }
-    }
-    if (!live) return;
-#pragma unroll
-    for (int n = 0; n < N; ++n)
-#pragma unroll
-        for (int kk = 0; kk < KC; ++kk) {
-            const int k = k0 + kk;
-            if (k < K) {
-                float* dst = part + (((((size_t)b * n_chunks + chunk) * N + n) * K + k) * 2) * a.Tp + t0;
-                *reinterpret_cast<float2*>(dst) = make_float2(num0[n][kk], num1[n][kk]);
-                *reinterpret_cast<float2*>(dst + a.Tp) = make_float2(den0[n][kk], den1[n][kk]);
-            }
-        }
-}
-
-// Stage 2: fixed-order sum over the chunks (deterministic), then V <- V (num/den)^q, in place.
-__global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, const float* part, float* act, int N, int n_chunks) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)a.B * N * a.K * a.Tp;
-    if (idx >= total) return;
-    const int t = (int)(idx % a.Tp);
-    long long r = idx / a.Tp;
-    const int k = (int)(r % a.K);
-    r /= a.K;
-    const int n = (int)(r % N);
-    const int b = (int)(r / N);
-    if (t >= a.T) {
-        act[idx] = 0.f;
-        return;
-    }
-    const bool sel = a.sel_m < 0 || n == a.sel_m || n == a.sel_n;
-    if (!sel) return;
-    float num = 0.f, den = 0.f;
-    for (int c = 0; c < n_chunks; ++c) {
-        const float* src = part + (((((size_t)b * n_chunks + c) * N + n) * a.K + k) * 2) * a.Tp + t;
-        num += src[0];
-        den += src[a.Tp];
-    }
-    den = den < a.eps ? a.eps : den;
-    act[idx] = act[idx] * pow_q(num / den, a.q_exp);
-}
-
-template <int C, int KC, bool FROM_Y>
-int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act) {
-    const int n_kc = (a.K + KC - 1) / KC;
-    const int n_slabs = (a.Tp + 63) / 64;
-    // enough warps to fill the machine a few times over, but chunks of at least 4 bins
-    long long want = (long long)h->n_sm * 24;
-    long long per_chunk_items = (long long)a.B * n_slabs * n_kc;
-    int n_chunks = (int)cdiv(want, per_chunk_items);
-    if (n_chunks < 1) n_chunks = 1;
-    int bins_per_chunk = (int)cdiv(a.F, n_chunks);
-    if (bins_per_chunk < 4) bins_per_chunk = a.F < 4 ? a.F : 4;
-    n_chunks = (int)cdiv(a.F, bins_per_chunk);
-    const size_t need = (size_t)a.B * n_chunks * C * a.K * 2 * a.Tp;
-    if (need > h->part_elems) {
-        if (h->part) cudaFree(h->part);
-        h->part = nullptr;
-        BSS_CUDA(h, cudaMalloc(&h->part, need * sizeof(float)));
-        h->part_elems = need;
-    }
-    const long long n_items = per_chunk_items * n_chunks;
-    const int wpc = 4;
-    const size_t smem_bytes = (size_t)wpc * C * a.K * 64 * sizeof(float);
-    if (smem_bytes > (size_t)h->max_smem) return bss_fail(h, BSS_EINVAL, "source model: n_basis too large");
-    static bool attr_done = false;
-    if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_partial_kernel<C, KC, FROM_Y>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
-        attr_done = true;
-    }
-    mu_act_partial_kernel<C, KC, FROM_Y><<<(unsigned)cdiv(n_items, wpc), wpc * 32, smem_bytes, h->stream>>>(
-        a, h->part, n_chunks, bins_per_chunk, n_slabs, n_kc, n_items);
-    h->launches++;
-    BSS_CUDA(h, cudaGetLastError());
-    const long long total = (long long)a.B * C * a.K * a.Tp;
-    mu_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, act, C, n_chunks);
-    h->launches++;
-    BSS_CUDA(h, cudaGetLastError());
-    return BSS_OK;
 }
 
 // ------------------------------------------------------------------------------------------- normalisation
@@ -686,32 +357,6 @@ __global__ void __launch_bounds__(256) import_x_kernel(const TIn* in, cf* X, int
         case 8: { constexpr int CC_ = 8; CALL; } break;                                \
         default: return bss_fail(h, BSS_EINVAL, "n_channels must be between 2 and 8"); \
     }
-
-int launch_mu_basis(bss_handle* h, const MuArgs& a) {
-    int rc = BSS_OK;
-    const bool from_y = a.Y != nullptr;
-    if (a.K <= 2) {
-        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 2, true>(h, a))) }
-        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 2, false>(h, a))) }
-    } else {
-        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 4, true>(h, a))) }
-        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_basis_t<CC_, 4, false>(h, a))) }
-    }
-    return rc;
-}
-
-int launch_mu_act(bss_handle* h, const MuArgs& a, float* act) {
-    int rc = BSS_OK;
-    const bool from_y = a.Y != nullptr;
-    if (a.K <= 2) {
-        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, true>(h, a, act))) }
-        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, false>(h, a, act))) }
-    } else {
-        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, true>(h, a, act))) }
-        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, false>(h, a, act))) }
-    }
-    return rc;
-}
 
 int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, const double* pw, int B, int N, int C, int F, int K,
                            double domain, double eps, double* aux_out) {
