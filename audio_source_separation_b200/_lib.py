@@ -56,6 +56,7 @@ SIGNATURES = {
     'bss_set_update_pair': (_i, [_vp, _i, _i]),
     'bss_update_once': (_i, [_vp]),
     'bss_run': (_i, [_vp, _i]),
+    'bss_run_record': (_i, [_vp, _i, ctypes.POINTER(_d)]),
     'bss_loss': (_i, [_vp, ctypes.POINTER(_d)]),
     'bss_separate': (_i, [_vp, _vp, _i, _i]),
     'bss_separate_device': (_i, [_vp, _vp, _i]),
@@ -198,6 +199,13 @@ class Handle:
 
     def run(self, n_iter):
         self._check(self._lib.bss_run(self._h, int(n_iter)))
+
+    def run_record(self, n_iter):
+        """n_iter updates with the loss after each one; returns (n_iter, B)."""
+        n_iter = int(n_iter)
+        out = (ctypes.c_double * (max(n_iter, 1) * self.B))()
+        self._check(self._lib.bss_run_record(self._h, n_iter, out))
+        return np.array(out[:n_iter * self.B], dtype=np.float64).reshape(n_iter, self.B)
 
     def loss(self):
         out = (ctypes.c_double * self.B)()

@@ -155,7 +155,8 @@ void bss_destroy(bss_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->X,   h->Y,    h->W,     h->Wf,    h->basis, h->basis2, h->act,     h->latent, h->U,      h->Cx,
                     h->gate, h->flags, h->pw,   h->scale, h->wfr,   h->wraw,   h->order,   h->logdet, h->aux,    h->G2,
-                    h->part, h->iw,   h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2};
+                    h->part, h->iw,   h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
+                    h->nz,   h->nt,   h->nv,    h->npart, h->loss_hist};
     for (void* p : bufs)
         if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -270,6 +271,35 @@ int bss_run(bss_handle* h, int n_iter) {
         BSS_TRY(bss_update_once(h));
     }
     return BSS_OK;
+}
+
+// one loss evaluation queued on the stream; result at lossbuf[B*F .. B*F+B)
+static int loss_device(bss_handle* h) {
+    if (is_nmf(h->cfg.method)) return nmf_loss(h);
+    if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    return h->cfg.method == BSS_FAST_MNMF ? mnmf_loss(h) : bss_loss_device(h);
+}
+
+int bss_run_record(bss_handle* h, int n_iter, double* loss) {
+    if (!h || n_iter < 0 || !loss) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t need = (size_t)(n_iter > 0 ? n_iter : 1) * h->B;
+    if (need > h->loss_hist_elems) {
+        if (h->loss_hist) cudaFree(h->loss_hist);
+        h->loss_hist = nullptr;
+        h->loss_hist_elems = 0;
+        BSS_CUDA(h, cudaMalloc(&h->loss_hist, need * sizeof(double)));
+        h->loss_hist_elems = need;
+    }
+    for (int i = 0; i < n_iter; ++i) {
+        BSS_TRY(bss_run(h, 1));
+        BSS_TRY(loss_device(h));
+        BSS_CUDA(h, cudaMemcpyAsync(h->loss_hist + (size_t)i * h->B, h->lossbuf + (size_t)h->B * h->F, sizeof(double) * h->B,
+                                    cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (n_iter > 0)
+        BSS_CUDA(h, cudaMemcpyAsync(loss, h->loss_hist, sizeof(double) * h->B * n_iter, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h);
 }
 
 int bss_loss(bss_handle* h, double* loss) {

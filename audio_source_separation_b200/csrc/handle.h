@@ -69,8 +69,16 @@ struct bss_handle {
     float* xt = nullptr;           // [B][F][M][Tp] |Q x|^2
     float* mn_acc = nullptr;       // numerator / denominator accumulators
     float* mn_acc2 = nullptr;
-    // NMF
-    float* target = nullptr;       // [B][F][Tp]
+    // NMF (fp64 throughout): target [B][F][T], factors [B][F][K] and [B][K][T]
+    float* target = nullptr;       // unused legacy slot
+    double* nz = nullptr;
+    double* nt = nullptr;
+    double* nv = nullptr;
+    double* npart = nullptr;       // partial sums of the activation update
+    size_t npart_elems = 0;
+    // loss history of bss_run_record: [n_iter][B]
+    double* loss_hist = nullptr;
+    size_t loss_hist_elems = 0;
 };
 
 #define BSS_CUDA(h, call)                                                                              \
@@ -228,4 +236,16 @@ int launch_cross_cov(bss_handle* h, const cf* Y, const cf* X, double2* G, long l
 int launch_scale_y(bss_handle* h, cf* Y, float* basis, const double* aux, const double2* scale, int B, int N, int F, int Tp, int K,
                    double domain);
 int launch_aux_from_power(bss_handle* h, const double* pw, double* aux, int B, int N, int F, double eps);
+// single-channel NMF (kernels_nmf.cu)
+struct NmfMath {
+    int kind;          // 0 EUC, 1 KL, 2 IS, 3 t, 4 Cauchy
+    int alg;           // enum bss_nmf_algorithm
+    double a, b, p, q; // exponents of the update (see methods_nmf.cu)
+    double nu, eps;
+    double loss_expo;  // 2 / domain
+    double loss_eps;
+};
+int launch_nmf_update(bss_handle* h, const NmfMath& m, const double* Z, double* Tm, double* V, int B, int F, int T, int K);
+int launch_nmf_loss(bss_handle* h, const NmfMath& m, const double* Z, const double* Tm, const double* V, double* terms, int B, int F,
+                    int T, int K);
 int launch_sum_frames(bss_handle* h, const float* raw, int B, int N, int T, int Tp, int kind, double coef, double eps, double* out);

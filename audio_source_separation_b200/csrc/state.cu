@@ -35,6 +35,20 @@ int get_rows(bss_handle* h, const float* dev, double* dst, size_t rows, int T, i
     return BSS_OK;
 }
 
+// NMF state is fp64 on the device: plain copies
+int put_f64(bss_handle* h, double* dev, const void* src, size_t n) {
+    if (!dev) return bss_fail(h, BSS_EINVAL, "this model has no such state");
+    BSS_CUDA(h, cudaMemcpyAsync(dev, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BSS_OK;
+}
+int get_f64(bss_handle* h, const double* dev, void* dst, size_t n) {
+    if (!dev) return bss_fail(h, BSS_EINVAL, "this model has no such state");
+    BSS_CUDA(h, cudaMemcpyAsync(dst, dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return BSS_OK;
+}
+
 size_t basis_rows(const bss_handle* h) {
     if (is_nmf(h->cfg.method) || h->cfg.partitioning) return (size_t)h->B * h->F;
     return (size_t)h->B * h->N * h->F;
@@ -51,6 +65,18 @@ extern "C" {
 int bss_set_state(bss_handle* h, int which, const void* src, int dtype) {
     if (!h || !src) return BSS_EINVAL;
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (is_nmf(h->cfg.method)) {
+        if (dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "NMF state is exchanged as float64");
+        switch (which) {
+            case BSS_STATE_TARGET:
+                BSS_TRY(put_f64(h, h->nz, src, (size_t)h->B * h->F * h->T));
+                h->has_input = true;
+                return BSS_OK;
+            case BSS_STATE_BASIS: return put_f64(h, h->nt, src, (size_t)h->B * h->F * h->K);
+            case BSS_STATE_ACTIVATION: return put_f64(h, h->nv, src, (size_t)h->B * h->K * h->T);
+        }
+        return bss_fail(h, BSS_EINVAL, "state cannot be set");
+    }
     switch (which) {
         case BSS_STATE_DEMIX_FILTER:
         case BSS_STATE_DIAGONALIZER: {
@@ -90,6 +116,15 @@ int bss_set_state(bss_handle* h, int which, const void* src, int dtype) {
 int bss_get_state(bss_handle* h, int which, void* dst, int dtype) {
     if (!h || !dst) return BSS_EINVAL;
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (is_nmf(h->cfg.method)) {
+        if (dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "NMF state is exchanged as float64");
+        switch (which) {
+            case BSS_STATE_TARGET: return get_f64(h, h->nz, dst, (size_t)h->B * h->F * h->T);
+            case BSS_STATE_BASIS: return get_f64(h, h->nt, dst, (size_t)h->B * h->F * h->K);
+            case BSS_STATE_ACTIVATION: return get_f64(h, h->nv, dst, (size_t)h->B * h->K * h->T);
+        }
+        return bss_fail(h, BSS_EINVAL, "unknown state");
+    }
     switch (which) {
         case BSS_STATE_DEMIX_FILTER:
         case BSS_STATE_DIAGONALIZER: {

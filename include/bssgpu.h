@@ -155,6 +155,10 @@ int bss_update_once(bss_handle* h);
  * range(iteration)` loop of __call__, src/bss/ilrma.py:233, with recordable_loss=False and no
  * callbacks); advances the IP2 pair schedule itself */
 int bss_run(bss_handle* h, int n_iter);
+/* the same loop with the loss recorded after every iteration, as the reference does by default
+ * (recordable_loss=True: src/bss/ilrma.py:239-241; NMFbase.update: src/algorithm/nmf.py:169-174): the
+ * per-iteration losses are reduced on the device and copied back once at the end.  loss[n_iter][B]. */
+int bss_run_record(bss_handle* h, int n_iter, double* loss);
 /* Model.compute_negative_loglikelihood() (src/bss/ilrma.py:648,993; src/bss/iva.py:604,783;
  * src/bss/mnmf.py:890) or the NMF criterion (src/algorithm/nmf.py:172-174); loss[B] */
 int bss_loss(bss_handle* h, double* loss);
