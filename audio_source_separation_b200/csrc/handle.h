@@ -53,7 +53,7 @@ struct bss_handle {
     int32_t* order = nullptr;      // [B][F][2] IP2 eigenvalue order
     double* logdet = nullptr;      // [B][F]
     double* aux = nullptr;         // [B][N] power-normalisation factors of the last update
-    double2* G2 = nullptr;         // [B][F][N][C] cross covariance Y X^H / T (ISS filter recovery)
+    double2* G2x = nullptr;        // [B][F][N][C] cross covariance Y X^H / T (ISS filter recovery)
     float* part = nullptr;         // partial sums of the cross-bin reductions
     size_t part_elems = 0;
     float* iw = nullptr;           // [B][F][NW][Tp] explicit inverse weights (generic covariance path)
@@ -66,6 +66,7 @@ struct bss_handle {
     float* latent2 = nullptr;      // scratch for the partitioned latent update
     // FastMNMF
     float* G = nullptr;            // [B][N][F][M]
+    float* G2 = nullptr;           // double buffer of G (the spatial update reads all sources of the old one)
     float* xt = nullptr;           // [B][F][M][Tp] |Q x|^2
     float* mn_acc = nullptr;       // numerator / denominator accumulators
     float* mn_acc2 = nullptr;
@@ -248,4 +249,12 @@ struct NmfMath {
 int launch_nmf_update(bss_handle* h, const NmfMath& m, const double* Z, double* Tm, double* V, int B, int F, int T, int K);
 int launch_nmf_loss(bss_handle* h, const NmfMath& m, const double* Z, const double* Tm, const double* V, double* terms, int B, int F,
                     int T, int K);
+// FastMNMF (kernels_mnmf.cu)
+int launch_mnmf_basis(bss_handle* h);
+int launch_mnmf_act(bss_handle* h);
+int launch_mnmf_scm(bss_handle* h);
+int launch_mnmf_weights(bss_handle* h);
+int launch_mnmf_loss_terms(bss_handle* h);
+int launch_mnmf_separate(bss_handle* h, cf* out);
+int launch_mnmf_normalize(bss_handle* h);
 int launch_sum_frames(bss_handle* h, const float* raw, int B, int N, int T, int Tp, int kind, double coef, double eps, double* out);

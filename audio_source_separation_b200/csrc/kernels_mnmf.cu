@@ -1,0 +1,876 @@
+// FastMNMF (src/bss/mnmf.py:637-946): jointly-diagonalisable multichannel NMF.
+//   x~[f,t,m] = |sum_c Q[f,m,c] x[c,f,t]|^2,  Lambda[n,f,t] = sum_k W[n,f,k] H[n,k,t],
+//   R[f,t,m]  = max(sum_n Lambda[n,f,t] g[n,f,m], eps)
+// None of x~, Lambda, R (each (F,T,M)-sized, 134 MB at cfg4) nor the reference's (N,F,T,M) broadcast
+// temporaries (1.07 GB) is stored: every kernel recomputes them from the staged bin tile of X and the
+// small factors.  One warp owns a bin; lanes own frame pairs; per-bin parameters (Q, g, W rows) sit in
+// the warp's shared-memory scratch and are read as broadcasts.
+//   basis W      per-bin reduction over frames            mnmf.py:790-800
+//   activation H cross-bin, two deterministic stages      mnmf.py:802-813
+//   spatial g    per-bin reduction over frames            mnmf.py:832-844
+//   weights 1/R  for the diagonaliser's covariances       mnmf.py:867-868
+//   normalise    mnmf.py:753-767,  loss :890-917,  separate (multichannel Wiener filter) :919-946
+#include "handle.h"
+#include "smallmat.cuh"
+
+namespace {
+
+constexpr int MN_STAGES = 3;
+constexpr int MN_SLAB = 128;
+constexpr int MN_NMAX = 8;     // sources
+constexpr int MN_KC = 2;       // basis vectors accumulated per pass
+constexpr int MN_NG = 2;       // sources per item of the spatial update
+
+struct MnArgs {
+    const cf* X;          // [B][F][M][Tp]
+    const cf* Qf;         // [B][F][M][M]
+    const float* G;       // [B][N][F][M]
+    const float* basis;   // [B][N][F][K]
+    const float* act;     // [B][N][K][Tp]
+    int B, F, M, N, T, Tp, K;
+    float eps;
+};
+
+struct MnParams {
+    MnArgs a;
+    TileGeom g;
+    long long n_items;
+    int per_bin;          // items per bin
+    uint32_t scratch_off, scratch_stride, ring_off;
+    float* out_f;         // basis_out / G_out
+    double* out_d;        // loss terms
+    cf* out_c;            // separated output
+    const cf* qinv;       // [B][F][M] row `reference_id` of Q^-1
+};
+
+// scratch (floats): Qs [2 M M] | gs [N M] | tb [N K] | red [64]
+template <int M>
+__device__ __forceinline__ void mn_scratch(float* base, int N, int K, float*& Qs, float*& gs, float*& tb, float*& red) {
+    Qs = base;
+    gs = Qs + 2 * M * M;
+    tb = gs + MN_NMAX * M;
+    red = tb + MN_NMAX * K;
+}
+template <int M>
+static inline size_t mn_scratch_bytes(int K) {
+    return (size_t)(2 * M * M + MN_NMAX * M + MN_NMAX * K + 64) * sizeof(float);
+}
+
+template <int M>
+__device__ __forceinline__ void mn_load_bin(const MnArgs& a, long long bf, int b, int f, float* Qs, float* gs, float* tb, int lane) {
+    const cf* q = a.Qf + (size_t)bf * M * M;
+    for (int i = lane; i < M * M; i += 32) reinterpret_cast<float2*>(Qs)[i] = __ldg(q + i);
+    for (int i = lane; i < a.N * M; i += 32) {
+        const int n = i / M, m = i - n * M;
+        gs[i] = __ldg(a.G + (((size_t)b * a.N + n) * a.F + f) * M + m);
+    }
+    for (int i = lane; i < a.N * a.K; i += 32) {
+        const int n = i / a.K, k = i - n * a.K;
+        tb[i] = __ldg(a.basis + (((size_t)b * a.N + n) * a.F + f) * a.K + k);
+    }
+    __syncwarp();
+}
+
+// y_m = sum_c Q[m][c] x_c for the two frames held in xv
+template <int M>
+__device__ __forceinline__ void mn_project(const float4 (&xv)[M], const float* Qs, float2 (&y0)[M], float2 (&y1)[M]) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            const float2 w = reinterpret_cast<const float2*>(Qs)[m * M + c];
+            const float2 x0 = make_float2(xv[c].x, xv[c].y), x1 = make_float2(xv[c].z, xv[c].w);
+            const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
+            a0 = __ffma2_rn(x0, wx, a0);
+            a0 = __ffma2_rn(make_float2(-x0.y, x0.x), wy, a0);
+            a1 = __ffma2_rn(x1, wx, a1);
+            a1 = __ffma2_rn(make_float2(-x1.y, x1.x), wy, a1);
+        }
+        y0[m] = a0;
+        y1[m] = a1;
+    }
+}
+
+template <int M>
+__device__ __forceinline__ void mn_power(const float4 (&xv)[M], const float* Qs, float2 (&xt)[M]) {
+    float2 y0[M], y1[M];
+    mn_project<M>(xv, Qs, y0, y1);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const float2 s0 = __fmul2_rn(y0[m], y0[m]), s1 = __fmul2_rn(y1[m], y1[m]);
+        xt[m] = make_float2(s0.x + s0.y, s1.x + s1.y);
+    }
+}
+
+// Lambda[n] for the frame pair at hrow = act + b N K Tp + t
+__device__ __forceinline__ void mn_lambda(const MnArgs& a, const float* tb, const float* hrow, float2 (&lam)[MN_NMAX]) {
+#pragma unroll
+    for (int n = 0; n < MN_NMAX; ++n) {
+        float2 l = make_float2(0.f, 0.f);
+        if (n < a.N) {
+            for (int k = 0; k < a.K; ++k) {
+                const float2 hv = __ldg(reinterpret_cast<const float2*>(hrow + ((size_t)n * a.K + k) * a.Tp));
+                const float tk = tb[n * a.K + k];
+                l = __ffma2_rn(hv, make_float2(tk, tk), l);
+            }
+        }
+        lam[n] = l;
+    }
+}
+
+// raw[m] = sum_n Lambda[n] g[n][m]
+template <int M>
+__device__ __forceinline__ void mn_variance(const MnArgs& a, const float* gs, const float2 (&lam)[MN_NMAX], float2 (&raw)[M]) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < MN_NMAX; ++n)
+            if (n < a.N) {
+                const float g = gs[n * M + m];
+                r = __ffma2_rn(lam[n], make_float2(g, g), r);
+            }
+        raw[m] = r;
+    }
+}
+
+__device__ __forceinline__ float2 floor2(float2 v, float eps) { return make_float2(fmaxf(v.x, eps), fmaxf(v.y, eps)); }
+__device__ __forceinline__ float2 rcp2n(float2 v) { return make_float2(__frcp_rn(v.x), __frcp_rn(v.y)); }
+
+// ------------------------------------------------------------------------------------------- basis W
+// item = (bin, chunk of MN_KC basis vectors)
+template <int M>
+__global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MnArgs& a = p.a;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    WarpStream<MN_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
+             (long long)gridDim.x * wpc, p.n_items, p.per_bin, lane);
+    const int row_stride = p.g.row_stride;
+    float2 num[MN_NMAX][MN_KC], den[MN_NMAX][MN_KC];
+#pragma unroll
+    for (int n = 0; n < MN_NMAX; ++n)
+#pragma unroll
+        for (int kk = 0; kk < MN_KC; ++kk) num[n][kk] = den[n][kk] = make_float2(0.f, 0.f);
+    int b = 0, f = 0, k0 = 0;
+    long long bf = 0;
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        if (st.first_slab()) {
+            bf = st.cons.item / p.per_bin;
+            k0 = (int)(st.cons.item - bf * p.per_bin) * MN_KC;
+            b = (int)(bf / a.F);
+            f = (int)(bf - (long long)b * a.F);
+            __syncwarp();
+            mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+        }
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            float2 xt[M];
+            mn_power<M>(xv, Qs, xt);
+            const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
+            float2 lam[MN_NMAX];
+            mn_lambda(a, tb, hrow, lam);
+            float2 R[M];
+            mn_variance<M>(a, gs, lam, R);
+            float2 u[M], ri[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                ri[m] = rcp2n(floor2(R[m], a.eps));
+                u[m] = __fmul2_rn(xt[m], __fmul2_rn(ri[m], ri[m]));
+            }
+#pragma unroll
+            for (int n = 0; n < MN_NMAX; ++n)
+                if (n < a.N) {
+                    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float g = gs[n * M + m];
+                        sa = __ffma2_rn(u[m], make_float2(g, g), sa);
+                        sb = __ffma2_rn(ri[m], make_float2(g, g), sb);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < MN_KC; ++kk)
+                        if (k0 + kk < a.K) {
+                            const float2 hv = __ldg(reinterpret_cast<const float2*>(hrow + ((size_t)n * a.K + k0 + kk) * a.Tp));
+                            num[n][kk] = __ffma2_rn(sa, hv, num[n][kk]);
+                            den[n][kk] = __ffma2_rn(sb, hv, den[n][kk]);
+                        }
+                }
+        }
+        if (st.last_slab()) {
+            constexpr int MP = MN_NMAX * MN_KC * 2;   // 32
+            float flat[MP];
+#pragma unroll
+            for (int n = 0; n < MN_NMAX; ++n)
+#pragma unroll
+                for (int kk = 0; kk < MN_KC; ++kk) {
+                    flat[(n * MN_KC + kk) * 2] = num[n][kk].x + num[n][kk].y;
+                    flat[(n * MN_KC + kk) * 2 + 1] = den[n][kk].x + den[n][kk].y;
+                    num[n][kk] = den[n][kk] = make_float2(0.f, 0.f);
+                }
+            warp_reduce_scatter<MP>(flat, lane);
+            // lane L holds element L: (n, kk, which) = (L / 4, (L / 2) % 2, L % 2)
+            const float mine = flat[0];
+            const float other = __shfl_down_sync(BSS_FULL, mine, 1);
+            const int n = lane / (2 * MN_KC), kk = (lane >> 1) % MN_KC, k = k0 + kk;
+            if ((lane & 1) == 0 && n < a.N && k < a.K) {
+                const float dn = fmaxf(other, a.eps);
+                const size_t idx = (((size_t)b * a.N + n) * a.F + f) * a.K + k;
+                p.out_f[idx] = a.basis[idx] * sqrtf(mine / dn);
+            }
+        }
+        st.release();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- activation H
+// Stage 1: a warp owns 64 frames of one mixture and walks a chunk of bins; part [B][n_chunks][N][K][2][Tp]
+template <int M>
+__global__ void __launch_bounds__(128) mnmf_act_partial_kernel(const MnArgs a, float* part, int n_chunks, int bins_per_chunk,
+                                                              int n_slabs, int n_kc, long long n_items, uint32_t scratch_stride) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const long long item = (long long)blockIdx.x * wpc + warp;
+    if (item >= n_items) return;
+    long long r = item;
+    const int kc = (int)(r % n_kc);
+    r /= n_kc;
+    const int slab = (int)(r % n_slabs);
+    r /= n_slabs;
+    const int chunk = (int)(r % n_chunks);
+    const int b = (int)(r / n_chunks);
+    const int k0 = kc * MN_KC;
+    const int t0 = slab * 64 + 2 * lane;
+    const bool live = t0 < a.Tp;
+    const int tl = live ? t0 : 0;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + (size_t)warp * scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    float2 num[MN_NMAX][MN_KC], den[MN_NMAX][MN_KC];
+#pragma unroll
+    for (int n = 0; n < MN_NMAX; ++n)
+#pragma unroll
+        for (int kk = 0; kk < MN_KC; ++kk) num[n][kk] = den[n][kk] = make_float2(0.f, 0.f);
+    const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tl;
+    const int f_begin = chunk * bins_per_chunk;
+    const int f_end = min(a.F, f_begin + bins_per_chunk);
+#pragma unroll 1
+    for (int f = f_begin; f < f_end; ++f) {
+        const long long bf = (long long)b * a.F + f;
+        __syncwarp();
+        mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+        float4 xv[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c)
+            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(a.X + ((size_t)bf * M + c) * a.Tp + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 xt[M];
+        mn_power<M>(xv, Qs, xt);
+        float2 lam[MN_NMAX];
+        mn_lambda(a, tb, hrow, lam);
+        float2 R[M];
+        mn_variance<M>(a, gs, lam, R);
+        float2 u[M], ri[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            ri[m] = rcp2n(floor2(R[m], a.eps));
+            u[m] = __fmul2_rn(xt[m], __fmul2_rn(ri[m], ri[m]));
+        }
+#pragma unroll
+        for (int n = 0; n < MN_NMAX; ++n)
+            if (n < a.N) {
+                float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const float g = gs[n * M + m];
+                    sa = __ffma2_rn(u[m], make_float2(g, g), sa);
+                    sb = __ffma2_rn(ri[m], make_float2(g, g), sb);
+                }
+#pragma unroll
+                for (int kk = 0; kk < MN_KC; ++kk)
+                    if (k0 + kk < a.K) {
+                        const float w = tb[n * a.K + k0 + kk];
+                        num[n][kk] = __ffma2_rn(sa, make_float2(w, w), num[n][kk]);
+                        den[n][kk] = __ffma2_rn(sb, make_float2(w, w), den[n][kk]);
+                    }
+            }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int n = 0; n < MN_NMAX; ++n)
+#pragma unroll
+        for (int kk = 0; kk < MN_KC; ++kk) {
+            const int k = k0 + kk;
+            if (n < a.N && k < a.K) {
+                float* dst = part + (((((size_t)b * n_chunks + chunk) * a.N + n) * a.K + k) * 2) * a.Tp + t0;
+                *reinterpret_cast<float2*>(dst) = num[n][kk];
+                *reinterpret_cast<float2*>(dst + a.Tp) = den[n][kk];
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256) mnmf_act_finish_kernel(const MnArgs a, const float* part, float* act, int n_chunks) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)a.B * a.N * a.K * a.Tp;
+    if (idx >= total) return;
+    const int t = (int)(idx % a.Tp);
+    long long r = idx / a.Tp;
+    const int k = (int)(r % a.K);
+    r /= a.K;
+    const int n = (int)(r % a.N);
+    const int b = (int)(r / a.N);
+    if (t >= a.T) {
+        act[idx] = 0.f;
+        return;
+    }
+    float num = 0.f, den = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+        const float* src = part + (((((size_t)b * n_chunks + c) * a.N + n) * a.K + k) * 2) * a.Tp + t;
+        num += src[0];
+        den += src[a.Tp];
+    }
+    den = fmaxf(den, a.eps);
+    act[idx] = act[idx] * sqrtf(num / den);
+}
+
+// ------------------------------------------------------------------------------------------- spatial g
+// item = (bin, group of MN_NG sources):  g[n,f,m] *= sqrt(sum_t Lambda x~/R^2 / max(sum_t Lambda/R, eps))
+template <int M>
+__global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MnArgs& a = p.a;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    WarpStream<MN_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
+             (long long)gridDim.x * wpc, p.n_items, p.per_bin, lane);
+    const int row_stride = p.g.row_stride;
+    float2 A[MN_NG][M], Bq[MN_NG][M];
+#pragma unroll
+    for (int j = 0; j < MN_NG; ++j)
+#pragma unroll
+        for (int m = 0; m < M; ++m) A[j][m] = Bq[j][m] = make_float2(0.f, 0.f);
+    int b = 0, f = 0, n0 = 0;
+    long long bf = 0;
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        if (st.first_slab()) {
+            bf = st.cons.item / p.per_bin;
+            n0 = (int)(st.cons.item - bf * p.per_bin) * MN_NG;
+            b = (int)(bf / a.F);
+            f = (int)(bf - (long long)b * a.F);
+            __syncwarp();
+            mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+        }
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            float2 xt[M];
+            mn_power<M>(xv, Qs, xt);
+            const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
+            float2 lam[MN_NMAX];
+            mn_lambda(a, tb, hrow, lam);
+            float2 R[M];
+            mn_variance<M>(a, gs, lam, R);
+            float2 u[M], ri[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                ri[m] = rcp2n(floor2(R[m], a.eps));
+                u[m] = __fmul2_rn(xt[m], __fmul2_rn(ri[m], ri[m]));
+            }
+#pragma unroll
+            for (int j = 0; j < MN_NG; ++j) {
+                // Lambda of source n0 + j (compile-time indexed select keeps lam[] in registers)
+                float2 l = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int n = 0; n < MN_NMAX; ++n)
+                    if (n == n0 + j) l = lam[n];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    A[j][m] = __ffma2_rn(l, u[m], A[j][m]);
+                    Bq[j][m] = __ffma2_rn(l, ri[m], Bq[j][m]);
+                }
+            }
+        }
+        if (st.last_slab()) {
+            constexpr int MV = MN_NG * M * 2;
+            constexpr int MP = (MV + 31) / 32 * 32;
+            constexpr int Q = MP / 32;
+            float flat[MP];
+#pragma unroll
+            for (int i = 0; i < MP; ++i) flat[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < MN_NG; ++j)
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    flat[(j * M + m) * 2] = A[j][m].x + A[j][m].y;
+                    flat[(j * M + m) * 2 + 1] = Bq[j][m].x + Bq[j][m].y;
+                    A[j][m] = Bq[j][m] = make_float2(0.f, 0.f);
+                }
+            warp_reduce_scatter<MP>(flat, lane);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) red[Q * lane + q] = flat[q];
+            __syncwarp();
+            for (int i = lane; i < MN_NG * M; i += 32) {
+                const int j = i / M, m = i - j * M, n = n0 + j;
+                if (n < a.N) {
+                    const float av = red[2 * i];
+                    const float bv = fmaxf(red[2 * i + 1], a.eps);
+                    const size_t idx = (((size_t)b * a.N + n) * a.F + f) * M + m;
+                    p.out_f[idx] = a.G[idx] * sqrtf(av / bv);
+                }
+            }
+            __syncwarp();
+        }
+        st.release();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- weights 1/R
+// iw [B][F][M][Tp]: inverse of the floored variance (no pass over X needed)
+template <int M>
+__global__ void __launch_bounds__(128) mnmf_weights_kernel(const MnArgs a, float* iw, long long n_items, int n_slabs,
+                                                          uint32_t scratch_stride) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long bf = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (bf >= n_items) return;
+    const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + (size_t)warp * scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+    for (int t = 2 * lane; t < a.Tp; t += 64) {
+        float2 lam[MN_NMAX];
+        mn_lambda(a, tb, a.act + (size_t)b * a.N * a.K * a.Tp + t, lam);
+        float2 R[M];
+        mn_variance<M>(a, gs, lam, R);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            *reinterpret_cast<float2*>(iw + ((size_t)bf * M + m) * a.Tp + t) = rcp2n(floor2(R[m], a.eps));
+    }
+}
+
+// ------------------------------------------------------------------------------------------- loss
+// per bin: sum_{t<T, m} (x~ + eps)/(y~ + eps) + log(y~ + eps), y~ unfloored     mnmf.py:907-915
+template <int M>
+__global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MnArgs& a = p.a;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    WarpStream<MN_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
+             (long long)gridDim.x * wpc, p.n_items, 1, lane);
+    const int row_stride = p.g.row_stride;
+    double total = 0.0;
+    int b = 0, f = 0;
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        const long long bf = st.cons.item;
+        if (st.first_slab()) {
+            b = (int)(bf / a.F);
+            f = (int)(bf - (long long)b * a.F);
+            __syncwarp();
+            mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+            total = 0.0;
+        }
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+        float part = 0.f;
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            float2 xt[M];
+            mn_power<M>(xv, Qs, xt);
+            const int t = tbase + tt;
+            float2 lam[MN_NMAX];
+            mn_lambda(a, tb, a.act + (size_t)b * a.N * a.K * a.Tp + t, lam);
+            float2 R[M];
+            mn_variance<M>(a, gs, lam, R);
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const float y0 = R[m].x + a.eps, y1 = R[m].y + a.eps;
+                if (t < a.T) part += (xt[m].x + a.eps) / y0 + logf(y0);
+                if (t + 1 < a.T) part += (xt[m].y + a.eps) / y1 + logf(y1);
+            }
+        }
+        total += (double)part;
+        if (st.last_slab()) {
+            const double s = warp_sum(total);
+            if (lane == 0) p.out_d[bf] = s;
+        }
+        st.release();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- separate
+// x^[n,f,t] = sum_m Qinv[ref][m] (Qx)[m] Lambda[n] g[n][m] / max(sum_n' Lambda g, eps)      mnmf.py:923-946
+template <int M>
+__global__ void __launch_bounds__(256, 1) mnmf_separate_kernel(const MnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MnArgs& a = p.a;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    WarpStream<MN_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
+             (long long)gridDim.x * wpc, p.n_items, 1, lane);
+    const int row_stride = p.g.row_stride;
+    int b = 0, f = 0;
+    float2 qi[M];
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next();
+        const long long bf = st.cons.item;
+        if (st.first_slab()) {
+            b = (int)(bf / a.F);
+            f = (int)(bf - (long long)b * a.F);
+            __syncwarp();
+            mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+#pragma unroll
+            for (int m = 0; m < M; ++m) qi[m] = __ldg(p.qinv + (size_t)bf * M + m);
+        }
+        const cf* xs = st.acquire();
+        const int nf = st.frames();
+        const int tbase = st.frame0();
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            float2 y0[M], y1[M];
+            mn_project<M>(xv, Qs, y0, y1);
+            const int t = tbase + tt;
+            float2 lam[MN_NMAX];
+            mn_lambda(a, tb, a.act + (size_t)b * a.N * a.K * a.Tp + t, lam);
+            float2 R[M];
+            mn_variance<M>(a, gs, lam, R);
+            // z[m] = Qinv[ref][m] * y[m] / y~[m]
+            float2 z0[M], z1[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const float2 ri = rcp2n(floor2(R[m], a.eps));
+                z0[m] = make_float2((qi[m].x * y0[m].x - qi[m].y * y0[m].y) * ri.x, (qi[m].x * y0[m].y + qi[m].y * y0[m].x) * ri.x);
+                z1[m] = make_float2((qi[m].x * y1[m].x - qi[m].y * y1[m].y) * ri.y, (qi[m].x * y1[m].y + qi[m].y * y1[m].x) * ri.y);
+            }
+#pragma unroll
+            for (int n = 0; n < MN_NMAX; ++n)
+                if (n < a.N) {
+                    float2 o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float g = gs[n * M + m];
+                        o0 = __ffma2_rn(z0[m], make_float2(g, g), o0);
+                        o1 = __ffma2_rn(z1[m], make_float2(g, g), o1);
+                    }
+                    cf* o = p.out_c + (((size_t)b * a.N + n) * a.F + f) * a.T + t;
+                    if (t < a.T) o[0] = cf_make(o0.x * lam[n].x, o0.y * lam[n].x);
+                    if (t + 1 < a.T) o[1] = cf_make(o1.x * lam[n].y, o1.y * lam[n].y);
+                }
+        }
+        st.release();
+    }
+}
+
+// row `ref` of Q^-1 per bin, fp64 -> complex64
+template <int M>
+__global__ void __launch_bounds__(64) mnmf_qinv_kernel(const double2* Qg, cf* out, long long n_bins, int ref, int32_t* flags) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_bins) return;
+    Mat<M> Q, Qi;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            const double2 v = Qg[(size_t)idx * M * M + i * M + j];
+            Q.a[i][j] = cd_make(v.x, v.y);
+        }
+    if (!mat_inverse(Q, Qi)) atomicAdd(flags, 1);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        cd v = Qi.a[0][m];
+#pragma unroll
+        for (int r = 1; r < M; ++r)
+            if (r == ref) v = Qi.a[r][m];
+        out[(size_t)idx * M + m] = cf_make((float)v.x, (float)v.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- normalisation
+// per bin: s = max(mean_m sum_c |Q[m][c]|^2, eps); Q /= sqrt(s); g /= s; gamma[n] = max(sum_m g, eps); g /= gamma;
+// W[n,f,:] *= gamma          mnmf.py:753-762
+__global__ void __launch_bounds__(128) mnmf_norm_bin_kernel(double2* Q, cf* Qf, float* G, float* basis, int B, int N, int F, int M,
+                                                           int K, double eps) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * F) return;
+    const int b = (int)(idx / F), f = (int)(idx - (long long)b * F);
+    double2* q = Q + (size_t)idx * M * M;
+    double s = 0.0;
+    for (int i = 0; i < M * M; ++i) s += q[i].x * q[i].x + q[i].y * q[i].y;
+    s /= (double)M;
+    if (s < eps) s = eps;
+    const double is = 1.0 / sqrt(s);
+    for (int i = 0; i < M * M; ++i) {
+        double2 v = q[i];
+        v.x *= is;
+        v.y *= is;
+        q[i] = v;
+        Qf[(size_t)idx * M * M + i] = cf_make((float)v.x, (float)v.y);
+    }
+    for (int n = 0; n < N; ++n) {
+        float* g = G + (((size_t)b * N + n) * F + f) * M;
+        double gv[8];
+        double sum = 0.0;
+        for (int m = 0; m < M; ++m) {
+            gv[m] = (double)g[m] / s;
+            sum += gv[m];
+        }
+        if (sum < eps) sum = eps;
+        for (int m = 0; m < M; ++m) g[m] = (float)(gv[m] / sum);
+        float* w = basis + (((size_t)b * N + n) * F + f) * K;
+        for (int k = 0; k < K; ++k) w[k] = (float)((double)w[k] * sum);
+    }
+}
+
+// block per (b, n, k): omega = max(sum_f W[n,f,k], eps); W /= omega; H[n,k,:] *= omega       mnmf.py:764-767
+__global__ void __launch_bounds__(256) mnmf_norm_basis_kernel(float* basis, float* act, int N, int F, int K, int Tp, double eps) {
+    __shared__ double red[8];
+    __shared__ double omega_s;
+    const long long bnk = blockIdx.x;
+    const int k = (int)(bnk % K);
+    const long long bn = bnk / K;
+    float* w = basis + (size_t)bn * F * K + k;
+    double s = 0.0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) s += (double)w[(size_t)f * K];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        omega_s = t < eps ? eps : t;
+    }
+    __syncthreads();
+    const double om = omega_s;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) w[(size_t)f * K] = (float)((double)w[(size_t)f * K] / om);
+    float* hh = act + (size_t)bnk * Tp;
+    for (int t = threadIdx.x; t < Tp; t += blockDim.x) hh[t] = (float)((double)hh[t] * om);
+}
+
+template <int M, typename Kern>
+int launch_stream(bss_handle* h, Kern kern, MnParams& p, int per_bin, int slab, int max_wpc) {
+    p.g = make_tile_geom(M, p.a.Tp, slab);
+    p.per_bin = per_bin;
+    p.n_items = (long long)p.a.B * p.a.F * per_bin;
+    StreamPlan sp;
+    if (!plan_stream(h, p.g, MN_STAGES, mn_scratch_bytes<M>(p.a.K), p.n_items, max_wpc, &sp))
+        return bss_fail(h, BSS_EINVAL, "FastMNMF: frame tile does not fit in shared memory");
+    p.scratch_off = sp.scratch_off;
+    p.scratch_stride = sp.scratch_stride;
+    p.ring_off = sp.ring_off;
+    BSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+    kern<<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+MnArgs mn_args(bss_handle* h) {
+    MnArgs a{};
+    a.X = h->X;
+    a.Qf = h->Wf;
+    a.G = h->G;
+    a.basis = h->basis;
+    a.act = h->act;
+    a.B = h->B;
+    a.F = h->F;
+    a.M = h->C;
+    a.N = h->N;
+    a.T = h->T;
+    a.Tp = h->Tp;
+    a.K = h->K;
+    a.eps = (float)h->cfg.eps;
+    return a;
+}
+
+template <int M>
+int mn_update_basis(bss_handle* h) {
+    MnParams p{};
+    p.a = mn_args(h);
+    p.out_f = h->basis2;
+    const int n_kc = (int)cdiv(h->K, MN_KC);
+    BSS_TRY((launch_stream<M>(h, mnmf_basis_kernel<M>, p, n_kc, MN_SLAB, 8)));
+    float* t = h->basis;
+    h->basis = h->basis2;
+    h->basis2 = t;
+    return BSS_OK;
+}
+
+template <int M>
+int mn_update_act(bss_handle* h) {
+    const MnArgs a = mn_args(h);
+    const int n_kc = (int)cdiv(a.K, MN_KC);
+    const int n_slabs = (a.Tp + 63) / 64;
+    long long want = (long long)h->n_sm * 16;
+    long long per_chunk_items = (long long)a.B * n_slabs * n_kc;
+    int n_chunks = (int)cdiv(want, per_chunk_items);
+    if (n_chunks < 1) n_chunks = 1;
+    int bins_per_chunk = (int)cdiv(a.F, n_chunks);
+    if (bins_per_chunk < 4) bins_per_chunk = a.F < 4 ? a.F : 4;
+    n_chunks = (int)cdiv(a.F, bins_per_chunk);
+    const size_t need = (size_t)a.B * n_chunks * a.N * a.K * 2 * a.Tp;
+    if (need > h->part_elems) {
+        if (h->part) cudaFree(h->part);
+        h->part = nullptr;
+        h->part_elems = 0;
+        BSS_CUDA(h, cudaMalloc(&h->part, need * sizeof(float)));
+        h->part_elems = need;
+    }
+    const long long n_items = per_chunk_items * n_chunks;
+    const int wpc = 4;
+    const uint32_t stride = (uint32_t)round_up((int)mn_scratch_bytes<M>(a.K), 16);
+    BSS_CUDA(h, cudaFuncSetAttribute(mnmf_act_partial_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+    mnmf_act_partial_kernel<M><<<(unsigned)cdiv(n_items, wpc), wpc * 32, (size_t)wpc * stride, h->stream>>>(
+        a, h->part, n_chunks, bins_per_chunk, n_slabs, n_kc, n_items, stride);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    const long long total = (long long)a.B * a.N * a.K * a.Tp;
+    mnmf_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, h->act, n_chunks);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+template <int M>
+int mn_update_scm(bss_handle* h) {
+    MnParams p{};
+    p.a = mn_args(h);
+    p.out_f = h->G2;
+    BSS_TRY((launch_stream<M>(h, mnmf_scm_kernel<M>, p, (int)cdiv(h->N, MN_NG), MN_SLAB, 8)));
+    float* t = h->G;
+    h->G = h->G2;
+    h->G2 = t;
+    return BSS_OK;
+}
+
+template <int M>
+int mn_weights(bss_handle* h) {
+    const MnArgs a = mn_args(h);
+    const long long n_items = (long long)a.B * a.F;
+    const int wpc = 4;
+    const uint32_t stride = (uint32_t)round_up((int)mn_scratch_bytes<M>(a.K), 16);
+    mnmf_weights_kernel<M><<<(unsigned)cdiv(n_items, wpc), wpc * 32, (size_t)wpc * stride, h->stream>>>(a, h->iw, n_items, 0, stride);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+template <int M>
+int mn_loss(bss_handle* h) {
+    MnParams p{};
+    p.a = mn_args(h);
+    p.out_d = h->lossbuf;
+    return launch_stream<M>(h, mnmf_loss_kernel<M>, p, 1, MN_SLAB, 8);
+}
+
+template <int M>
+int mn_separate(bss_handle* h, cf* out) {
+    const long long n_bins = (long long)h->B * h->F;
+    cf* qinv = reinterpret_cast<cf*>(h->scale);   // [B][N][F] double2 >= [B][F][M] float2 when N >= 1 ... sized in mnmf_allocate
+    mnmf_qinv_kernel<M><<<(unsigned)cdiv(n_bins, 64), 64, 0, h->stream>>>(h->W, qinv, n_bins, h->cfg.reference_id, h->flags);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    MnParams p{};
+    p.a = mn_args(h);
+    p.out_c = out;
+    p.qinv = qinv;
+    return launch_stream<M>(h, mnmf_separate_kernel<M>, p, 1, MN_SLAB, 8);
+}
+
+}  // namespace
+
+#define MN_DISPATCH(Mval, CALL)                                                        \
+    switch (Mval) {                                                                    \
+        case 2: { constexpr int MM_ = 2; CALL; } break;                                \
+        case 3: { constexpr int MM_ = 3; CALL; } break;                                \
+        case 4: { constexpr int MM_ = 4; CALL; } break;                                \
+        case 5: { constexpr int MM_ = 5; CALL; } break;                                \
+        case 6: { constexpr int MM_ = 6; CALL; } break;                                \
+        case 7: { constexpr int MM_ = 7; CALL; } break;                                \
+        case 8: { constexpr int MM_ = 8; CALL; } break;                                \
+        default: return bss_fail(h, BSS_EINVAL, "n_channels must be between 2 and 8"); \
+    }
+
+int launch_mnmf_basis(bss_handle* h) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_update_basis<MM_>(h)))
+    return rc;
+}
+int launch_mnmf_act(bss_handle* h) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_update_act<MM_>(h)))
+    return rc;
+}
+int launch_mnmf_scm(bss_handle* h) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_update_scm<MM_>(h)))
+    return rc;
+}
+int launch_mnmf_weights(bss_handle* h) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_weights<MM_>(h)))
+    return rc;
+}
+int launch_mnmf_loss_terms(bss_handle* h) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_loss<MM_>(h)))
+    return rc;
+}
+int launch_mnmf_separate(bss_handle* h, cf* out) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_separate<MM_>(h, out)))
+    return rc;
+}
+int launch_mnmf_normalize(bss_handle* h) {
+    const long long n_bins = (long long)h->B * h->F;
+    mnmf_norm_bin_kernel<<<(unsigned)cdiv(n_bins, 128), 128, 0, h->stream>>>(h->W, h->Wf, h->G, h->basis, h->B, h->N, h->F, h->C, h->K,
+                                                                            h->cfg.eps);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    mnmf_norm_basis_kernel<<<(unsigned)((long long)h->B * h->N * h->K), 256, 0, h->stream>>>(h->basis, h->act, h->N, h->F, h->K, h->Tp,
+                                                                                            h->cfg.eps);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}

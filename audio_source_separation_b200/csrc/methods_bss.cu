@@ -170,7 +170,7 @@ int bss_allocate(bss_handle* h) {
     }
     if (is_iss(h)) {
         BSS_TRY(dalloc(h, &h->Y, B * F * N * Tp));
-        BSS_TRY(dalloc(h, &h->G2, B * F * N * C));
+        BSS_TRY(dalloc(h, &h->G2x, B * F * N * C));
     }
     return BSS_OK;
 }
@@ -202,9 +202,9 @@ int bss_refresh_estimates(bss_handle* h) {
 
 int bss_filter_from_estimates(bss_handle* h) {
     if (!h->Y || !h->y_valid) return bss_fail(h, BSS_ESTATE, "no estimates to derive a filter from");
-    if (!h->G2) BSS_TRY(dalloc(h, &h->G2, (size_t)h->B * h->F * h->N * h->C));
-    BSS_TRY(launch_cross_cov(h, h->Y, h->X, h->G2, (long long)h->B * h->F, h->C, h->T, h->Tp));
-    BSS_TRY(launch_lsq_filter(h, h->G2, h->Cx, h->W, (long long)h->B * h->F, h->C));
+    if (!h->G2x) BSS_TRY(dalloc(h, &h->G2x, (size_t)h->B * h->F * h->N * h->C));
+    BSS_TRY(launch_cross_cov(h, h->Y, h->X, h->G2x, (long long)h->B * h->F, h->C, h->T, h->Tp));
+    BSS_TRY(launch_lsq_filter(h, h->G2x, h->Cx, h->W, (long long)h->B * h->F, h->C));
     return launch_sync_wf(h, h->W, h->Wf, (long long)h->B * h->F * h->N * h->C);
 }
 
