@@ -165,12 +165,16 @@ class AuxIVAbase(IVAbase):
 
         self._run_callbacks()
 
-        if not self.recordable_loss and self.callbacks is None:
+        if self.callbacks is None:
             self._check_spatial()
             self._push()
             if self.algorithm_spatial in ['pairwise', 'IP2'] and self.update_pair is not None:
                 self._handle.set_update_pair(*self.update_pair)
-            self._handle.run(iteration)
+            if self.recordable_loss:
+                # the loss after every iteration is reduced on the device and fetched once
+                self.loss.extend(float(v) for v in self._handle.run_record(iteration)[:, 0])
+            else:
+                self._handle.run(iteration)
             if self.algorithm_spatial in ['pairwise', 'IP2']:
                 for _ in range(iteration):
                     self._select_update_pair(tell_device=False)

@@ -64,6 +64,9 @@ struct bss_handle {
     size_t pinned_bytes = 0;
 
     float* latent2 = nullptr;      // scratch for the partitioned latent update
+    float* beff = nullptr;         // [B][N][F][K]  partitioned model: Z[n,k] T[f,k]
+    float* aeff = nullptr;         // [B][N][K][Tp] partitioned model: V[k,t] replicated per source
+    float* praw = nullptr;         // [B][N][F][K][2] raw statistics of the basis kernel
     // FastMNMF
     float* G = nullptr;            // [B][N][F][M]
     float* G2 = nullptr;           // double buffer of G (the spatial update reads all sources of the old one)
@@ -212,9 +215,10 @@ struct MuArgs {
     float p_exp, q_exp;   // (d+2)/d and d/(d+2)
     float nu, eps;
     int sel_m, sel_n;     // >= 0: pairwise source model, only these two sources move
+    float* raw;           // non-null: basis kernel stores the raw (num, den) sums [B][N][F][K][2] instead of updating
 };
 int launch_mu_basis(bss_handle* h, const MuArgs& a);
-int launch_mu_act(bss_handle* h, const MuArgs& a, float* act);
+int launch_mu_act(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_out = nullptr);
 int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, const double* pw, int B, int N, int C, int F, int K,
                            double domain, double eps, double* aux_out);
 int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const double2* scale, int B, int N, int C, int F, int K,
@@ -249,6 +253,12 @@ struct NmfMath {
 int launch_nmf_update(bss_handle* h, const NmfMath& m, const double* Z, double* Tm, double* V, int B, int F, int T, int K);
 int launch_nmf_loss(bss_handle* h, const NmfMath& m, const double* Z, const double* Tm, const double* V, double* terms, int B, int F,
                     int T, int K);
+// partitioned ILRMA (kernels_part.cu)
+int launch_part_expand(bss_handle* h);
+int launch_part_latent(bss_handle* h);
+int launch_part_basis(bss_handle* h);
+int launch_part_act_finish(bss_handle* h, int n_chunks);
+int launch_part_normalize(bss_handle* h);
 // FastMNMF (kernels_mnmf.cu)
 int launch_mnmf_basis(bss_handle* h);
 int launch_mnmf_act(bss_handle* h);

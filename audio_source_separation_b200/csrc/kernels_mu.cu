@@ -206,6 +206,11 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
                     const float nm = red[2 * i];
                     const float dn = fmaxf(red[2 * i + 1], a.eps);
                     const size_t idx = (((size_t)b * N + n) * a.F + f) * K + k;
+                    if (a.raw) {   // partitioned model: the caller combines the raw statistics across sources / bins
+                        a.raw[2 * idx] = nm;
+                        a.raw[2 * idx + 1] = red[2 * i + 1];
+                        continue;
+                    }
                     const float told = a.basis[idx];
                     const bool sel = a.sel_m < 0 || n == a.sel_m || n == a.sel_n;
                     a.basis_out[idx] = sel ? told * pow_q(nm / dn, a.q_exp) : told;
@@ -383,8 +388,9 @@ __global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, cons
     act[idx] = act[idx] * pow_q(num / den, a.q_exp);
 }
 
+// act == nullptr: stage 1 only (the partial sums stay in h->part, *n_chunks_out tells how many)
 template <int C, int KC, bool KFIX, bool FROM_Y>
-int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act) {
+int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_out) {
     const int n_kc = KFIX ? 1 : (a.K + KC - 1) / KC;
     const int n_slabs = (a.Tp + 63) / 64;
     // enough warps to fill the machine a few times over, but chunks of at least 4 bins
@@ -417,6 +423,8 @@ int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act) {
         a, h->part, n_chunks, bins_per_chunk, n_slabs, n_kc, n_items);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
+    if (n_chunks_out) *n_chunks_out = n_chunks;
+    if (!act) return BSS_OK;
     const long long total = (long long)a.B * C * a.K * a.Tp;
     mu_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, act, C, n_chunks);
     h->launches++;
@@ -451,15 +459,15 @@ int launch_mu_basis(bss_handle* h, const MuArgs& a) {
     return rc;
 }
 
-int launch_mu_act(bss_handle* h, const MuArgs& a, float* act) {
+int launch_mu_act(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_out) {
     int rc = BSS_OK;
     const bool from_y = a.Y != nullptr;
     if (a.K == 2) {
-        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, true, true>(h, a, act))) }
-        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, true, false>(h, a, act))) }
+        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, true, true>(h, a, act, n_chunks_out))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 2, true, false>(h, a, act, n_chunks_out))) }
     } else {
-        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, false, true>(h, a, act))) }
-        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, false, false>(h, a, act))) }
+        if (from_y) { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, false, true>(h, a, act, n_chunks_out))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_mu_act_t<CC_, 4, false, false>(h, a, act, n_chunks_out))) }
     }
     return rc;
 }

@@ -157,7 +157,9 @@ int bss_allocate(bss_handle* h) {
             BSS_TRY(dalloc(h, &h->act, B * K * Tp));
             BSS_TRY(dalloc(h, &h->latent, B * N * K));
             BSS_TRY(dalloc(h, &h->latent2, B * N * K));
-            BSS_TRY(dalloc(h, &h->iw, B * F * N * Tp));
+            BSS_TRY(dalloc(h, &h->beff, B * N * F * K));
+            BSS_TRY(dalloc(h, &h->aeff, B * N * K * Tp));
+            BSS_TRY(dalloc(h, &h->praw, B * N * F * K * 2));
         } else {
             BSS_TRY(dalloc(h, &h->basis, B * N * F * K));
             BSS_TRY(dalloc(h, &h->basis2, B * N * F * K));
@@ -210,7 +212,12 @@ int bss_filter_from_estimates(bss_handle* h) {
 
 int bss_covariance_only(bss_handle* h) {
     CovArgs c = cov_args(h);
-    if (h->cfg.method == BSS_GAUSS_ILRMA && !h->cfg.partitioning) {
+    if (h->cfg.method == BSS_GAUSS_ILRMA && h->cfg.partitioning) {
+        BSS_TRY(launch_part_expand(h));
+        c.basis = h->beff;
+        c.act = h->aeff;
+        c.wmode = WM_ILRMA;
+    } else if (h->cfg.method == BSS_GAUSS_ILRMA) {
         c.wmode = WM_ILRMA;
         c.expo = (float)(2.0 / h->cfg.domain);
     } else if (uses_model(h)) {

@@ -1,0 +1,122 @@
+"""CPU-only checks of the boundary and of the multi-GPU host logic:
+
+  * libbssgpu.so loads and exports every symbol include/bssgpu.h declares (no compute call is made);
+  * without a CUDA device the product fails loudly instead of falling back to a CPU path;
+  * the product package never imports the oracle;
+  * the batch sharding / final gather of the N > 1 path on world_size-2 `gloo` process groups.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'bssgpu.h')
+PKG = os.path.join(ROOT, 'audio_source_separation_b200')
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(bss_[a-z_0-9]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from audio_source_separation_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from audio_source_separation_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), "libbssgpu.so does not export " + name
+    # the ctypes table binds exactly the header's entry points
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.bss_version().decode().startswith('bssgpu')
+
+
+def test_config_struct_matches_header(lib):
+    """struct bss_config: 14 int32 followed by 4 doubles, no padding surprises."""
+    import ctypes
+    from audio_source_separation_b200 import _lib
+    assert ctypes.sizeof(_lib.Config) == 14 * 4 + 4 * 8
+    text = open(HEADER).read()
+    body = text[text.index('typedef struct bss_config {'):text.index('} bss_config;')]
+    fields = re.findall(r'\b(?:int32_t|double)\s+([a-z_]+);', body)
+    assert fields == [f[0] for f in _lib.Config._fields_]
+
+
+def test_no_cpu_fallback(lib):
+    """Here (no GPU) creating a handle must fail with a CUDA error, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from audio_source_separation_b200.bss.ilrma import GaussILRMA
+    from audio_source_separation_b200.algorithm.nmf import EUCNMF
+    X = (np.random.default_rng(0).standard_normal((2, 5, 8)) + 0j)
+    with pytest.raises(RuntimeError, match='no CUDA device'):
+        GaussILRMA(n_basis=2)(X, iteration=1)
+    with pytest.raises(RuntimeError, match='no CUDA device'):
+        EUCNMF(n_basis=2)(np.abs(X[0]), iteration=1)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), fn
+                assert '/root/reference' not in text, fn
+
+
+def test_shard_range_partitions_the_batch():
+    from audio_source_separation_b200.batch import shard_range
+    for n_items in (0, 1, 7, 64, 512, 513):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n_items, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n_items
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_range(512, 3, 8) == (192, 256)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from audio_source_separation_b200.batch import shard_range, gather_outputs
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group(backend='gloo')
+B, N, F, T = 6, 2, 5, 4
+full = (np.arange(B * N * F * T * 2, dtype=np.float32)).reshape(B, N, F, T, 2)
+lo, hi = shard_range(B, rank, world)
+local = torch.from_numpy(full[lo:hi].copy())          # what this rank's GPU would have separated
+out = gather_outputs(local, world)
+assert out.shape == (B, N, F, T, 2), out.shape
+assert np.array_equal(out.numpy(), full)               # rank order == batch order, bit exact
+dist.barrier()
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_gather_outputs_world_size_2_gloo(tmp_path):
+    """The only collective of the sharded path (all-gather of the separated outputs) on 2 CPU ranks."""
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29611', str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count('ok') == 2

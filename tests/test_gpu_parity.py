@@ -162,6 +162,40 @@ def test_gauss_ilrma_golden(cuda_device, name):
     assert model.estimation is out
 
 
+@pytest.mark.parametrize('spatial,K,C', [('IP', 2, 3), ('IP', 5, 4), ('ISS', 3, 2)])
+def test_gauss_ilrma_partitioned(cuda_device, spatial, K, C):
+    """Shared basis with latent source assignment (src/bss/ilrma.py:368-408, :313-320): golden fixture plus
+    oracle runs for ISS and for n_basis above / below the kernels' accumulation chunk."""
+    import warnings
+    from audio_source_separation_b200.bss.ilrma import GaussILRMA
+    meta, i, o = load_golden('ilrma_ip_power_part')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        model = GaussILRMA(n_basis=meta['n_basis'], partitioning=True)
+        out = model(i['X'], iteration=meta['iteration'], demix_filter=i['W0'], basis=i['T0'], activation=i['V0'], latent=i['Z0'])
+        assert rel(out, o['output']) < TOL_STATE
+        assert rel(model.basis, o['basis']) < TOL_STATE and rel(model.activation, o['activation']) < TOL_STATE
+        assert rel(model.demix_filter, o['demix_filter']) < TOL_STATE
+        _loss_close(model.loss, o['loss'])
+        F, T = 33, 61
+        X = synth.mix2(C, F, T, seed=C)
+        rng = np.random.default_rng(3)
+        W0 = np.tile(np.eye(C, dtype=np.complex128), (F, 1, 1))
+        T0 = rng.random((F, K)).astype(np.float32).astype(np.float64)
+        V0 = rng.random((K, T)).astype(np.float32).astype(np.float64)
+        Z0 = rng.random((C, K)).astype(np.float32).astype(np.float64)
+        Z0 = (Z0 / Z0.sum(axis=0)).astype(np.float32).astype(np.float64)
+        model = GaussILRMA(n_basis=K, partitioning=True, algorithm_spatial=spatial)
+        out = model(X, iteration=3, demix_filter=W0, basis=T0, activation=V0, latent=Z0)
+    want, st, loss = o_ilrma.run(X, iteration=3, n_basis=K, spatial=spatial, partitioning=True, W=W0, T=T0, V=V0, Z=Z0)
+    assert rel(out, want) < TOL_STATE
+    assert rel(model.basis, st['T']) < TOL_STATE and rel(model.activation, st['V']) < TOL_STATE
+    assert rel(model.latent, st['Z']) < TOL_STATE
+    _loss_close(model.loss, loss)
+    with pytest.raises(NotImplementedError):
+        GaussILRMA(n_basis=2, partitioning=True, normalize='projection-back', recordable_loss=False)(X, iteration=1)
+
+
 def test_gauss_ilrma_update_once_by_hand(cuda_device):
     """Users may drive update_once themselves after assigning input/state."""
     from audio_source_separation_b200.bss.ilrma import GaussILRMA
