@@ -109,22 +109,36 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[MP], int lane) {
     }
 }
 
+// ------------------------------------------------------------------------------ bin-tile layout
+// A bin tile [rows][Tp] (X: rows = channels, Y: rows = sources) is stored as consecutive blocks of
+// BSS_XSLAB frames: block s holds `rows` rows of L_s = min(BSS_XSLAB, Tp - s BSS_XSLAB) frames each.  Every
+// block (one ring stage) and the whole tile are contiguous in HBM, so a stage is filled by ONE bulk
+// copy and a warp that walks a bin reads 8 rows Tp bytes strictly sequentially.  Tp <= BSS_XSLAB
+// degenerates to the plain row-major tile.
+#define BSS_XSLAB 128
+__host__ __device__ __forceinline__ size_t tile_off(int rows, int Tp, int r, int t) {
+    const int t0 = t & ~(BSS_XSLAB - 1);
+    const int rest = Tp - t0;
+    const int L = rest < BSS_XSLAB ? rest : BSS_XSLAB;
+    return (size_t)t0 * rows + (size_t)r * L + (t - t0);
+}
+
 // ------------------------------------------------------------------------------ streaming ring
 // A warp walks a list of jobs (bin tile, frame slab); lane 0 keeps STAGES-1 bulk copies in
 // flight into the warp's private shared-memory ring while the whole warp consumes the oldest.
 struct TileGeom {
     int n_rows;        // rows per bin tile (channels or sources)
-    int row_len;       // padded frames per row in global memory (Tp)
-    int slab;          // frames per slab (== row_len when the tile is taken whole)
-    int n_slabs;       // slabs per tile
-    int row_stride;    // frames between rows inside a stage
+    int row_len;       // padded frames per row (Tp)
+    int slab;          // frames per block (BSS_XSLAB, or Tp when the tile is a single block)
+    int n_slabs;       // blocks per tile
+    int row_stride;    // unused by the kernels (rows of a staged block are frames() apart)
     uint32_t stage_bytes;
 };
 
 struct JobCursor {
-    long long item;    // flat item index
+    int item;          // flat item index (32 bit: the per-slab control path must stay cheap)
     int slab;
-    __device__ __forceinline__ void advance(long long stride, int n_slabs) {
+    __device__ __forceinline__ void advance(int stride, int n_slabs) {
         if (++slab == n_slabs) {
             slab = 0;
             item += stride;
@@ -137,21 +151,12 @@ __device__ __forceinline__ int slab_frames(const TileGeom& g, int slab) {
     return rest < g.slab ? rest : g.slab;
 }
 
-// issue the copies of one job; `tile` points at row 0, frame 0 of the bin tile in global memory
+// issue the copy of one job (one block of the tile, contiguous); `tile` points at the bin tile in global memory
 __device__ __forceinline__ void ring_issue(const TileGeom& g, const cf* tile, int slab, unsigned char* stage,
                                            uint64_t* bar) {
-    if (g.n_slabs == 1) {
-        const uint32_t bytes = (uint32_t)g.n_rows * (uint32_t)g.row_len * 8u;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(stage, tile, bytes, bar);
-    } else {
-        const int nf = slab_frames(g, slab);
-        const uint32_t bytes = (uint32_t)nf * 8u;
-        mbar_expect_tx(bar, bytes * (uint32_t)g.n_rows);
-        for (int r = 0; r < g.n_rows; ++r)
-            bulk_g2s(stage + (size_t)r * g.row_stride * 8, tile + (size_t)r * g.row_len + (size_t)slab * g.slab,
-                     bytes, bar);
-    }
+    const uint32_t bytes = (uint32_t)g.n_rows * (uint32_t)slab_frames(g, slab) * 8u;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(stage, tile + (size_t)slab * g.slab * g.n_rows, bytes, bar);
 }
 
 // Per-warp stream over (item, slab) jobs.  Items owned by a warp are first, first+stride, ...;
@@ -162,8 +167,8 @@ struct WarpStream {
     uint64_t* bars;
     unsigned char* ring;
     const cf* base;
-    size_t tile_elems;
-    long long n_items, stride;
+    uint32_t tile_elems;
+    int n_items, stride;
     int items_per_tile;
     JobCursor prod, cons;
     int pstage, cstage, lane;
@@ -172,20 +177,20 @@ struct WarpStream {
     __device__ __forceinline__ void issue_next() {
         if (prod.item < n_items) {
             if (lane == 0)
-                ring_issue(g, base + (size_t)(prod.item / items_per_tile) * tile_elems, prod.slab,
+                ring_issue(g, base + (size_t)(items_per_tile == 1 ? (uint32_t)prod.item : (uint32_t)prod.item / (uint32_t)items_per_tile) * tile_elems,
+                           prod.slab,
                            ring + (size_t)pstage * g.stage_bytes, &bars[pstage]);
             prod.advance(stride, g.n_slabs);
             pstage = (pstage + 1 == STAGES) ? 0 : pstage + 1;
         }
     }
     __device__ __forceinline__ void start(const TileGeom& geom, uint64_t* bars_, unsigned char* ring_, const cf* base_,
-                                          long long first, long long stride_, long long n_items_, int items_per_tile_,
-                                          int lane_) {
+                                          int first, int stride_, int n_items_, int items_per_tile_, int lane_) {
         g = geom;
         bars = bars_;
         ring = ring_;
         base = base_;
-        tile_elems = (size_t)geom.n_rows * geom.row_len;
+        tile_elems = (uint32_t)geom.n_rows * (uint32_t)geom.row_len;
         n_items = n_items_;
         stride = stride_;
         items_per_tile = items_per_tile_;
@@ -224,10 +229,9 @@ struct WarpStream {
     }
 };
 
-// host-side geometry of a [rows][Tp] bin tile: whole when small, 256-frame slabs otherwise
-#define BSS_SLAB_FRAMES 256
-#define BSS_WHOLE_TILE_BYTES 8192
-static inline TileGeom make_tile_geom(int rows, int Tp, int slab_frames = BSS_SLAB_FRAMES) {
+// host-side geometry of a [rows][Tp] bin tile: one block when Tp <= BSS_XSLAB, BSS_XSLAB-frame blocks otherwise
+static inline TileGeom make_tile_geom(int rows, int Tp, int slab_frames = BSS_XSLAB) {
+    slab_frames = BSS_XSLAB;   // fixed by the memory layout
     TileGeom g;
     g.n_rows = rows;
     g.row_len = Tp;

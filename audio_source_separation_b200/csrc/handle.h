@@ -141,7 +141,7 @@ static inline bool plan_stream(const bss_handle* h, const TileGeom& g, int stage
     const size_t per_warp = (size_t)stages * g.stage_bytes + scratch_stride + (size_t)stages * 8;
     int wpc = (int)(((size_t)h->max_smem - 512) / per_warp);
     if (wpc > max_wpc) wpc = max_wpc;
-    if (wpc < 1) return false;
+    if (wpc < 1 || n_items > 0x7fffffffLL) return false;   // the device-side cursors are 32 bit
     const uint32_t bars_bytes = (uint32_t)round_up(wpc * stages * 8, 128);
     out->wpc = wpc;
     out->scratch_off = bars_bytes;

@@ -81,9 +81,8 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
     float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);
     WarpStream<COV_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * COV_STAGES,
-             smem + p.ring_off + (size_t)warp * COV_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, p.n_groups, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * COV_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, p.n_groups, lane);
     const int Tp = a.Tp;
     const int K = KT > 0 ? KT : a.K;
 
@@ -103,10 +102,10 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
     while (st.active()) {
         st.issue_next();
         if (st.first_slab()) {
-            const long long bf = st.cons.item / p.n_groups;
-            const int grp = (int)(st.cons.item - bf * p.n_groups);
-            b = (int)(bf / a.F);
-            f = (int)(bf - (long long)b * a.F);
+            const int bf = st.cons.item / p.n_groups;
+            const int grp = st.cons.item - bf * p.n_groups;
+            b = bf / a.F;
+            f = bf - b * a.F;
             w0 = grp * NS;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             const int t = tbase + tt;
             float wa[NS], wb[NS];
 #pragma unroll
@@ -230,7 +229,7 @@ int launch_cov_t(bss_handle* h, const CovArgs& a) {
     p.inv_T = 1.0 / (double)a.T;
     if (p.n_items == 0) return BSS_OK;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, COV_STAGES, (size_t)NS * (a.K > 0 ? a.K : 1) * 4, p.n_items, COV_MAX_WARPS, &sp))
+    if (!plan_stream(h, p.g, COV_STAGES, (size_t)NS * (a.K > 0 ? a.K : 1) * 4, (int)p.n_items, COV_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "covariance: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;

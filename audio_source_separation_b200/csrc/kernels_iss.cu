@@ -99,11 +99,11 @@ __global__ void __launch_bounds__(256) iss_kernel(const IssParams p) {
 #pragma unroll
             for (int k = 0; k < N; ++k) ur[k] = ui[k] = d[k] = 0.f;
             for (int t = 2 * lane; t < Tp; t += 64) {
-                const float4 yn = *reinterpret_cast<const float4*>(y + (size_t)n * Tp + t);
+                const float4 yn = *reinterpret_cast<const float4*>(y + tile_off(N, Tp, n, t));
                 const float p0 = fmaf(yn.x, yn.x, yn.y * yn.y), p1 = fmaf(yn.z, yn.z, yn.w * yn.w);
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    const float4 yk = *reinterpret_cast<const float4*>(y + (size_t)k * Tp + t);
+                    const float4 yk = *reinterpret_cast<const float4*>(y + tile_off(N, Tp, k, t));
                     const float2 ri = *reinterpret_cast<const float2*>(rinv + (size_t)k * Tp + t);
                     // y_k conj(y_n) / r_k
                     ur[k] = fmaf(ri.x, fmaf(yk.x, yn.x, yk.y * yn.y), ur[k]);
@@ -129,16 +129,16 @@ __global__ void __launch_bounds__(256) iss_kernel(const IssParams p) {
                 }
             }
             for (int t = 2 * lane; t < Tp; t += 64) {
-                const float4 yn = *reinterpret_cast<const float4*>(y + (size_t)n * Tp + t);
+                const float4 yn = *reinterpret_cast<const float4*>(y + tile_off(N, Tp, n, t));
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    float4 yk = *reinterpret_cast<float4*>(y + (size_t)k * Tp + t);
+                    float4 yk = *reinterpret_cast<float4*>(y + tile_off(N, Tp, k, t));
                     // y_k -= v_k y_n
                     yk.x -= vr[k] * yn.x - vi[k] * yn.y;
                     yk.y -= vr[k] * yn.y + vi[k] * yn.x;
                     yk.z -= vr[k] * yn.z - vi[k] * yn.w;
                     yk.w -= vr[k] * yn.w + vi[k] * yn.z;
-                    *reinterpret_cast<float4*>(y + (size_t)k * Tp + t) = yk;
+                    *reinterpret_cast<float4*>(y + tile_off(N, Tp, k, t)) = yk;
                 }
             }
         }
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) iss_kernel(const IssParams p) {
             for (int n = 0; n < N; ++n) {
                 float s = 0.f;
                 for (int t = 2 * lane; t < Tp; t += 64) {
-                    const float4 yn = *reinterpret_cast<const float4*>(y + (size_t)n * Tp + t);
+                    const float4 yn = *reinterpret_cast<const float4*>(y + tile_off(N, Tp, n, t));
                     s += fmaf(yn.x, yn.x, yn.y * yn.y) + fmaf(yn.z, yn.z, yn.w * yn.w);
                 }
                 const double tot = warp_sum((double)s);
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(128) cross_cov_kernel(const cf* Y, const cf* X
         float4 xv[C], yv[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            xv[c] = __ldg(reinterpret_cast<const float4*>(X + ((size_t)bf * C + c) * Tp + t));
-            yv[c] = __ldg(reinterpret_cast<const float4*>(Y + ((size_t)bf * C + c) * Tp + t));
+            xv[c] = __ldg(reinterpret_cast<const float4*>(X + (size_t)bf * C * Tp + tile_off(C, Tp, c, t)));
+            yv[c] = __ldg(reinterpret_cast<const float4*>(Y + (size_t)bf * C * Tp + tile_off(C, Tp, c, t)));
         }
 #pragma unroll
         for (int n = 0; n < C; ++n)
@@ -222,10 +222,11 @@ __global__ void __launch_bounds__(256) scale_y_kernel(cf* Y, float* basis, const
         sy = (float)s.y;
         mag = hypot(s.x, s.y);
     }
-    cf* y = Y + (size_t)row * Tp;
+    cf* tile = Y + (size_t)bf * N * Tp;
     for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
-        const cf v = y[t];
-        y[t] = cf_make(v.x * sx - v.y * sy, v.x * sy + v.y * sx);
+        cf* y = tile + tile_off(N, Tp, n, t);
+        const cf v = *y;
+        *y = cf_make(v.x * sx - v.y * sy, v.x * sy + v.y * sx);
     }
     if (basis && threadIdx.x < K) {
         const double sc = domain == 2.0 ? mag * mag : pow(mag, domain);

@@ -150,24 +150,23 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, p.per_bin, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, p.per_bin, lane);
     float2 num[MN_NMAX][MN_KC], den[MN_NMAX][MN_KC];
 #pragma unroll
     for (int n = 0; n < MN_NMAX; ++n)
 #pragma unroll
         for (int kk = 0; kk < MN_KC; ++kk) num[n][kk] = den[n][kk] = make_float2(0.f, 0.f);
     int b = 0, f = 0, k0 = 0;
-    long long bf = 0;
+    int bf = 0;
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
-            k0 = (int)(st.cons.item - bf * p.per_bin) * MN_KC;
-            b = (int)(bf / a.F);
-            f = (int)(bf - (long long)b * a.F);
+            k0 = (st.cons.item - bf * p.per_bin) * MN_KC;
+            b = bf / a.F;
+            f = bf - b * a.F;
             __syncwarp();
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
         }
@@ -178,7 +177,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 xt[M];
             mn_power<M>(xv, Qs, xt);
             const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(128) mnmf_act_partial_kernel(const MnArgs a, f
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
-    const long long item = (long long)blockIdx.x * wpc + warp;
+    const long long item = (int)(blockIdx.x * wpc + warp);
     if (item >= n_items) return;
     long long r = item;
     const int kc = (int)(r % n_kc);
@@ -266,6 +265,8 @@ __global__ void __launch_bounds__(128) mnmf_act_partial_kernel(const MnArgs a, f
 #pragma unroll
         for (int kk = 0; kk < MN_KC; ++kk) num[n][kk] = den[n][kk] = make_float2(0.f, 0.f);
     const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tl;
+    const size_t xoff = tile_off(M, a.Tp, 0, tl);
+    const int xlen = (int)(tile_off(M, a.Tp, 1, tl) - xoff);
     const int f_begin = chunk * bins_per_chunk;
     const int f_end = min(a.F, f_begin + bins_per_chunk);
 #pragma unroll 1
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(128) mnmf_act_partial_kernel(const MnArgs a, f
         float4 xv[M];
 #pragma unroll
         for (int c = 0; c < M; ++c)
-            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(a.X + ((size_t)bf * M + c) * a.Tp + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)bf * M * a.Tp + xoff + (size_t)c * xlen)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float2 xt[M];
         mn_power<M>(xv, Qs, xt);
         float2 lam[MN_NMAX];
@@ -358,24 +359,23 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, p.per_bin, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, p.per_bin, lane);
     float2 A[MN_NG][M], Bq[MN_NG][M];
 #pragma unroll
     for (int j = 0; j < MN_NG; ++j)
 #pragma unroll
         for (int m = 0; m < M; ++m) A[j][m] = Bq[j][m] = make_float2(0.f, 0.f);
     int b = 0, f = 0, n0 = 0;
-    long long bf = 0;
+    int bf = 0;
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
-            n0 = (int)(st.cons.item - bf * p.per_bin) * MN_NG;
-            b = (int)(bf / a.F);
-            f = (int)(bf - (long long)b * a.F);
+            n0 = (st.cons.item - bf * p.per_bin) * MN_NG;
+            b = bf / a.F;
+            f = bf - b * a.F;
             __syncwarp();
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
         }
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 xt[M];
             mn_power<M>(xv, Qs, xt);
             const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(128) mnmf_weights_kernel(const MnArgs a, float
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long bf = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (bf >= n_items) return;
-    const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
+    const int b = (int)(bf / a.F), f = bf - b * a.F;
     float *Qs, *gs, *tb, *red;
     mn_scratch<M>(reinterpret_cast<float*>(smem + (size_t)warp * scratch_stride), a.N, a.K, Qs, gs, tb, red);
     mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
@@ -484,18 +484,17 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, 1, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
     double total = 0.0;
     int b = 0, f = 0;
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
-        const long long bf = st.cons.item;
+        const int bf = st.cons.item;
         if (st.first_slab()) {
-            b = (int)(bf / a.F);
-            f = (int)(bf - (long long)b * a.F);
+            b = bf / a.F;
+            f = bf - b * a.F;
             __syncwarp();
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
             total = 0.0;
@@ -508,7 +507,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 xt[M];
             mn_power<M>(xv, Qs, xt);
             const int t = tbase + tt;
@@ -544,18 +543,17 @@ __global__ void __launch_bounds__(256, 1) mnmf_separate_kernel(const MnParams p)
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, 1, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
     int b = 0, f = 0;
     float2 qi[M];
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
-        const long long bf = st.cons.item;
+        const int bf = st.cons.item;
         if (st.first_slab()) {
-            b = (int)(bf / a.F);
-            f = (int)(bf - (long long)b * a.F);
+            b = bf / a.F;
+            f = bf - b * a.F;
             __syncwarp();
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
 #pragma unroll
@@ -568,7 +566,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_separate_kernel(const MnParams p)
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 y0[M], y1[M];
             mn_project<M>(xv, Qs, y0, y1);
             const int t = tbase + tt;
@@ -694,7 +692,7 @@ int launch_stream(bss_handle* h, Kern kern, MnParams& p, int per_bin, int slab, 
     p.per_bin = per_bin;
     p.n_items = (long long)p.a.B * p.a.F * per_bin;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, MN_STAGES, mn_scratch_bytes<M>(p.a.K), p.n_items, max_wpc, &sp))
+    if (!plan_stream(h, p.g, MN_STAGES, mn_scratch_bytes<M>(p.a.K), (int)p.n_items, max_wpc, &sp))
         return bss_fail(h, BSS_EINVAL, "FastMNMF: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;

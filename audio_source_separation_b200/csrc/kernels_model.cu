@@ -139,15 +139,14 @@ __global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
     const int wpc = blockDim.x >> 5;
     WarpStream<MU_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
-             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, p.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, 1, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, p.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
     cf w[C][C];
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
-        const long long bf = st.cons.item;
-        const int b = (int)(bf / p.F), f = (int)(bf - (long long)b * p.F);
+        const int bf = st.cons.item;
+        const int b = bf / p.F, f = bf - b * p.F;
         if (st.first_slab()) {
             load_filter<C, false>(w, p.Wf + (size_t)bf * C * C);
             if (p.scale) {
@@ -170,7 +169,7 @@ __global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             const int t = tbase + tt;
 #pragma unroll
             for (int n = 0; n < C; ++n) {
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
                     cf_fma(y1, w[n][c], cf_make(xv[c].z, xv[c].w));
                 }
                 if (p.Y)
-                    *reinterpret_cast<float4*>(p.Y + ((size_t)bf * C + n) * p.Tp + t) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    *reinterpret_cast<float4*>(p.Y + (size_t)bf * C * p.Tp + tile_off(C, p.Tp, n, t)) = make_float4(y0.x, y0.y, y1.x, y1.y);
                 if (p.out) {
                     cf* o = p.out + (((size_t)b * C + n) * p.F + f) * p.T + t;
                     if (t < p.T) o[0] = y0;
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(256) export_y_kernel(const cf* Y, const double
     r /= F;
     const int n = (int)(r % N);
     const int b = (int)(r / N);
-    cf v = Y[(((size_t)b * F + f) * N + n) * Tp + t];
+    cf v = Y[((size_t)b * F + f) * N * Tp + tile_off(N, Tp, n, t)];
     if (scale) {
         const double2 sd = scale[((size_t)b * N + n) * F + f];
         const cf s = cf_make((float)sd.x, (float)sd.y);
@@ -236,15 +235,14 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
     WarpStream<MU_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
              smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
-             (long long)blockIdx.x * wpc + warp, (long long)gridDim.x * wpc, p.n_items, 1, lane);
-    const int row_stride = p.g.row_stride;
+             (int)(blockIdx.x * wpc + warp), (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
     cf w[C][C];
     double total = 0.0;
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
-        const long long bf = st.cons.item;
-        const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
+        const int bf = st.cons.item;
+        const int b = (int)(bf / a.F), f = bf - b * a.F;
         if (st.first_slab()) {
             for (int i = lane; i < N * K; i += 32) {
                 const int n = i / K, k = i - n * K;
@@ -262,7 +260,7 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float P0[C], P1[C];
             frame_power<C, FROM_Y>(xv, w, P0, P1);
             const int t = tbase + tt;
@@ -341,7 +339,7 @@ __global__ void __launch_bounds__(256) import_x_kernel(const TIn* in, cf* X, int
         const TIn s = in[(((size_t)b * C + c) * F + f) * T + t];
         v = cf_make((float)s.x, (float)s.y);
     }
-    X[idx] = v;
+    X[((size_t)b * F + f) * C * Tp + tile_off(C, Tp, c, t)] = v;
 }
 
 }  // namespace
@@ -399,7 +397,7 @@ static int launch_separate_t(bss_handle* h, const cf* X, const cf* Wf, const dou
     p.g = make_tile_geom(C, Tp);
     p.n_items = (long long)B * F;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, MU_STAGES, 16, p.n_items, 8, &sp))
+    if (!plan_stream(h, p.g, MU_STAGES, 16, (int)p.n_items, 8, &sp))
         return bss_fail(h, BSS_EINVAL, "separate: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
@@ -439,7 +437,7 @@ static int launch_ilrma_loss_t(bss_handle* h, const MuArgs& a, float expo, doubl
     p.g = make_tile_geom(C, a.Tp);
     p.n_items = (long long)a.B * a.F;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, MU_STAGES, (size_t)C * a.K * 4, p.n_items, 8, &sp))
+    if (!plan_stream(h, p.g, MU_STAGES, (size_t)C * a.K * 4, (int)p.n_items, 8, &sp))
         return bss_fail(h, BSS_EINVAL, "loss: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;

@@ -101,8 +101,7 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
     WarpStream<MU_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
              smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
-             (long long)blockIdx.x * wpc + warp, (long long)gridDim.x * wpc, p.n_items, p.n_kc, lane);
-    const int row_stride = p.g.row_stride;
+             (int)(blockIdx.x * wpc + warp), (int)(gridDim.x * wpc), (int)p.n_items, p.n_kc, lane);
 
     float2 num[N][KC], den[N][KC];
 #pragma unroll
@@ -118,10 +117,10 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
     while (st.active()) {
         st.issue_next();
         if (st.first_slab()) {
-            const long long bf = st.cons.item / p.n_kc;
-            k0 = (int)(st.cons.item - bf * p.n_kc) * KC;
-            b = (int)(bf / a.F);
-            f = (int)(bf - (long long)b * a.F);
+            const int bf = st.cons.item / p.n_kc;
+            k0 = (st.cons.item - bf * p.n_kc) * KC;
+            b = bf / a.F;
+            f = bf - b * a.F;
             vrow = a.act + (size_t)b * N * K * Tp;
             if (KFIX) {
 #pragma unroll
@@ -145,7 +144,7 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 P[C];
             frame_power2<C, FROM_Y>(xv, w, P);
             const int t = tbase + tt;
@@ -230,7 +229,7 @@ int launch_mu_basis_t(bss_handle* h, const MuArgs& a) {
     p.n_items = (long long)a.B * a.F * p.n_kc;
     constexpr int MP = (C * KC * 2 + 31) / 32 * 32;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, MU_STAGES, ((size_t)C * a.K + MP) * 4, p.n_items, MU_MAX_WARPS, &sp))
+    if (!plan_stream(h, p.g, MU_STAGES, ((size_t)C * a.K + MP) * 4, (int)p.n_items, MU_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "source model: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
@@ -257,7 +256,7 @@ __global__ void __launch_bounds__(128) mu_act_partial_kernel(const MuArgs a, flo
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
-    const long long item = (long long)blockIdx.x * wpc + warp;
+    const long long item = (int)(blockIdx.x * wpc + warp);
     if (item >= n_items) return;
     constexpr int N = C;
     const int K = KFIX ? KC : a.K;
@@ -301,13 +300,16 @@ __global__ void __launch_bounds__(128) mu_act_partial_kernel(const MuArgs a, flo
     const int f_begin = chunk * bins_per_chunk;
     const int f_end = min(a.F, f_begin + bins_per_chunk);
     const cf* src = FROM_Y ? a.Y : a.X;
+    // this lane's two frames inside the block-interleaved bin tile (common.cuh: tile_off)
+    const size_t xoff = tile_off(C, a.Tp, 0, live ? t0 : 0);
+    const int xlen = (int)(tile_off(C, a.Tp, 1, live ? t0 : 0) - xoff);
 #pragma unroll 2
     for (int f = f_begin; f < f_end; ++f) {
         const size_t bf = (size_t)b * a.F + f;
         float4 xv[C];
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(src + (bf * C + c) * a.Tp + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(src + bf * C * a.Tp + xoff + (size_t)c * xlen)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float2 w[C][C];
         load_filter<C, FROM_Y>(w, a.Wf + bf * C * C);
         float2 P[C];

@@ -47,12 +47,14 @@ __global__ void __launch_bounds__(128) frame_power_partial_kernel(const cf* src,
     for (int n = 0; n < C; ++n) s0[n] = s1[n] = 0.f;
     const int f_begin = chunk * bins_per_chunk;
     const int f_end = min(F, f_begin + bins_per_chunk);
+    const size_t xoff = tile_off(C, Tp, 0, t0);
+    const int xlen = (int)(tile_off(C, Tp, 1, t0) - xoff);
 #pragma unroll 2
     for (int f = f_begin; f < f_end; ++f) {
         const size_t bf = (size_t)b * F + f;
         float4 xv[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) xv[c] = __ldg(reinterpret_cast<const float4*>(src + (bf * C + c) * Tp + t0));
+        for (int c = 0; c < C; ++c) xv[c] = __ldg(reinterpret_cast<const float4*>(src + bf * C * Tp + xoff + (size_t)c * xlen));
         float P0[C], P1[C];
         power2<C, FROM_Y>(xv, Wf + bf * C * C, P0, P1);
 #pragma unroll
@@ -112,14 +114,13 @@ __global__ void __launch_bounds__(256) t_weights_kernel(const TwParams p) {
     float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);
     WarpStream<TW_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * TW_STAGES,
-             smem + p.ring_off + (size_t)warp * TW_STAGES * p.g.stage_bytes, p.X, (long long)blockIdx.x * wpc + warp,
-             (long long)gridDim.x * wpc, p.n_items, 1, lane);
-    const int row_stride = p.g.row_stride;
+             smem + p.ring_off + (size_t)warp * TW_STAGES * p.g.stage_bytes, p.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
 #pragma unroll 1
     while (st.active()) {
         st.issue_next();
-        const long long bf = st.cons.item;
-        const int b = (int)(bf / p.F), f = (int)(bf - (long long)b * p.F);
+        const int bf = st.cons.item;
+        const int b = bf / p.F, f = bf - b * p.F;
         if (st.first_slab()) {
             for (int i = lane; i < N * K; i += 32) {
                 const int n = i / K, k = i - n * K;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) t_weights_kernel(const TwParams p) {
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * row_stride + tt);
+            for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float P0[C], P1[C];
             power2<C, false>(xv, p.Wf + (size_t)bf * C * C, P0, P1);
             const int t = tbase + tt;
@@ -238,7 +239,7 @@ static int launch_t_weights_t(bss_handle* h, const cf* X, const cf* Wf, const fl
     p.g = make_tile_geom(C, Tp);
     p.n_items = (long long)B * F;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, TW_STAGES, (size_t)C * K * 4, p.n_items, 8, &sp))
+    if (!plan_stream(h, p.g, TW_STAGES, (size_t)C * K * 4, (int)p.n_items, 8, &sp))
         return bss_fail(h, BSS_EINVAL, "t weights: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
