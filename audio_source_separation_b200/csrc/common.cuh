@@ -159,41 +159,45 @@ __device__ __forceinline__ void ring_issue(const TileGeom& g, const cf* tile, in
     bulk_g2s(stage, tile + (size_t)slab * g.slab * g.n_rows, bytes, bar);
 }
 
-// Per-warp stream over (item, slab) jobs.  Items owned by a warp are first, first+stride, ...;
-// the bin tile of an item is tile index item / items_per_tile.
+// Per-warp stream over (item, slab) jobs.  Items owned by a warp are first, first+stride, ... < n_items;
+// the bin tile of an item is tile index item / items_per_tile.  Geometry, base pointer and items_per_tile are
+// passed to every call (they live in the kernel's constant parameter bank) so that the per-warp state is a
+// dozen 32-bit registers: the streaming kernels are register bound.
 template <int STAGES>
 struct WarpStream {
-    TileGeom g;
-    uint64_t* bars;
-    unsigned char* ring;
-    const cf* base;
-    uint32_t tile_elems;
-    int n_items, stride;
-    int items_per_tile;
     JobCursor prod, cons;
+    int n_items, stride;
+    uint32_t bars_sa;            // shared-space address of this warp's STAGES mbarriers
+    uint32_t ring_sa;            // shared-space address of this warp's ring
+    const unsigned char* ring;   // the same ring as a generic pointer (consumer loads)
     int pstage, cstage, lane;
     uint32_t cphase;
 
-    __device__ __forceinline__ void issue_next() {
+    __device__ __forceinline__ void issue_next(const TileGeom& g, const cf* base, int items_per_tile) {
         if (prod.item < n_items) {
-            if (lane == 0)
-                ring_issue(g, base + (size_t)(items_per_tile == 1 ? (uint32_t)prod.item : (uint32_t)prod.item / (uint32_t)items_per_tile) * tile_elems,
-                           prod.slab,
-                           ring + (size_t)pstage * g.stage_bytes, &bars[pstage]);
+            if (lane == 0) {
+                const uint32_t tile = items_per_tile == 1 ? (uint32_t)prod.item : (uint32_t)prod.item / (uint32_t)items_per_tile;
+                const uint32_t bytes = (uint32_t)g.n_rows * (uint32_t)slab_frames(g, prod.slab) * 8u;
+                const uint32_t bar = bars_sa + 8u * (uint32_t)pstage;
+                const cf* src = base + (size_t)tile * ((uint32_t)g.n_rows * (uint32_t)g.row_len) +
+                                (size_t)((uint32_t)prod.slab * (uint32_t)g.slab * (uint32_t)g.n_rows);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 ring_sa + (uint32_t)pstage * g.stage_bytes),
+                             "l"(src), "r"(bytes), "r"(bar)
+                             : "memory");
+            }
             prod.advance(stride, g.n_slabs);
             pstage = (pstage + 1 == STAGES) ? 0 : pstage + 1;
         }
     }
-    __device__ __forceinline__ void start(const TileGeom& geom, uint64_t* bars_, unsigned char* ring_, const cf* base_,
-                                          int first, int stride_, int n_items_, int items_per_tile_, int lane_) {
-        g = geom;
-        bars = bars_;
+    __device__ __forceinline__ void start(const TileGeom& g, uint64_t* bars_, unsigned char* ring_, const cf* base, int first,
+                                          int stride_, int n_items_, int items_per_tile, int lane_) {
+        bars_sa = smem_u32(bars_);
+        ring_sa = smem_u32(ring_);
         ring = ring_;
-        base = base_;
-        tile_elems = (uint32_t)geom.n_rows * (uint32_t)geom.row_len;
         n_items = n_items_;
         stride = stride_;
-        items_per_tile = items_per_tile_;
         lane = lane_;
         prod.item = cons.item = first;
         prod.slab = cons.slab = 0;
@@ -201,25 +205,35 @@ struct WarpStream {
         cphase = 0;
         if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bars_[s], 1);
             mbar_fence_init();
         }
         __syncwarp();
 #pragma unroll 1
-        for (int s = 0; s < STAGES - 1; ++s) issue_next();
+        for (int s = 0; s < STAGES - 1; ++s) issue_next(g, base, items_per_tile);
     }
     __device__ __forceinline__ bool active() const { return cons.item < n_items; }
-    // wait for the current job's tile; returns its shared-memory address
-    __device__ __forceinline__ const cf* acquire() {
-        mbar_wait(&bars[cstage], cphase);
-        return reinterpret_cast<const cf*>(ring + (size_t)cstage * g.stage_bytes);
+    // wait for the current job's block; returns its shared-memory address
+    __device__ __forceinline__ const cf* acquire(const TileGeom& g) {
+        const uint32_t bar = bars_sa + 8u * (uint32_t)cstage;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(cphase)
+                : "memory");
+        }
+        return reinterpret_cast<const cf*>(ring + (size_t)((uint32_t)cstage * g.stage_bytes));
     }
-    __device__ __forceinline__ int frames() const { return slab_frames(g, cons.slab); }
-    __device__ __forceinline__ int frame0() const { return cons.slab * g.slab; }
+    __device__ __forceinline__ int frames(const TileGeom& g) const { return slab_frames(g, cons.slab); }
+    __device__ __forceinline__ int frame0(const TileGeom& g) const { return cons.slab * g.slab; }
     __device__ __forceinline__ bool first_slab() const { return cons.slab == 0; }
-    __device__ __forceinline__ bool last_slab() const { return cons.slab == g.n_slabs - 1; }
+    __device__ __forceinline__ bool last_slab(const TileGeom& g) const { return cons.slab == g.n_slabs - 1; }
     // all lanes are done reading the current stage
-    __device__ __forceinline__ void release() {
+    __device__ __forceinline__ void release(const TileGeom& g) {
         __syncwarp();
         cons.advance(stride, g.n_slabs);
         if (++cstage == STAGES) {
@@ -228,6 +242,31 @@ struct WarpStream {
         }
     }
 };
+
+// A CTA walks a contiguous range of items (its warps interleave inside it): consecutive bins of one
+// mixture, so whatever is shared by the bins of a mixture can be cached per CTA.
+__device__ __forceinline__ void cta_item_range(int n_items, int& lo, int& hi) {
+    const int per_cta = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+    lo = (int)blockIdx.x * per_cta;
+    hi = min(n_items, lo + per_cta);
+}
+// Copy the activation rows (floats_per_mix = N K Tp floats per mixture, contiguous over mixtures) of the
+// mixtures touched by items [lo, hi) into shared memory; returns the first mixture.  The host guarantees
+// (plan_stream_cached) that the range spans at most two mixtures.  Ends with a CTA barrier.
+__device__ __forceinline__ int load_act_cache(float* cache, const float* act, int floats_per_mix, int lo, int hi, int items_per_bin,
+                                              int n_bins) {
+    int b_lo = 0;
+    if (lo < hi) {
+        b_lo = (lo / items_per_bin) / n_bins;
+        const int b_hi = ((hi - 1) / items_per_bin) / n_bins;
+        const int n2 = (b_hi - b_lo + 1) * (floats_per_mix >> 1);   // float2 elements (Tp is even)
+        const float2* src = reinterpret_cast<const float2*>(act + (size_t)b_lo * floats_per_mix);
+        float2* dst = reinterpret_cast<float2*>(cache);
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    return b_lo;
+}
 
 // host-side geometry of a [rows][Tp] bin tile: one block when Tp <= BSS_XSLAB, BSS_XSLAB-frame blocks otherwise
 static inline TileGeom make_tile_geom(int rows, int Tp, int slab_frames = BSS_XSLAB) {

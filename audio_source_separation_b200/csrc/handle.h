@@ -136,10 +136,11 @@ struct StreamPlan {
     unsigned grid;
 };
 static inline bool plan_stream(const bss_handle* h, const TileGeom& g, int stages, size_t scratch_per_warp,
-                               long long n_items, int max_wpc, StreamPlan* out) {
+                               long long n_items, int max_wpc, StreamPlan* out, size_t reserve_bytes = 0) {
     const uint32_t scratch_stride = (uint32_t)round_up((int)scratch_per_warp, 16);
     const size_t per_warp = (size_t)stages * g.stage_bytes + scratch_stride + (size_t)stages * 8;
-    int wpc = (int)(((size_t)h->max_smem - 512) / per_warp);
+    if ((size_t)h->max_smem < 1024 + reserve_bytes + per_warp) return false;
+    int wpc = (int)(((size_t)h->max_smem - 512 - reserve_bytes) / per_warp);
     if (wpc > max_wpc) wpc = max_wpc;
     if (wpc < 1 || n_items > 0x7fffffffLL) return false;   // the device-side cursors are 32 bit
     const uint32_t bars_bytes = (uint32_t)round_up(wpc * stages * 8, 128);
@@ -148,7 +149,7 @@ static inline bool plan_stream(const bss_handle* h, const TileGeom& g, int stage
     out->scratch_stride = scratch_stride;
     out->ring_off = (uint32_t)round_up((int)(bars_bytes + wpc * scratch_stride), 128);
     out->smem_bytes = out->ring_off + (size_t)wpc * stages * g.stage_bytes;
-    int ctas_per_sm = (int)((size_t)h->max_smem / (out->smem_bytes + 1024));
+    int ctas_per_sm = (int)((size_t)h->max_smem / (out->smem_bytes + reserve_bytes + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int by_threads = 2048 / (wpc * 32);
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
@@ -157,6 +158,22 @@ static inline bool plan_stream(const bss_handle* h, const TileGeom& g, int stage
     const long long cap = (long long)h->n_sm * ctas_per_sm;
     if (grid > cap) grid = cap;
     out->grid = (unsigned)grid;
+    return true;
+}
+
+// Same plan with room for a per-CTA cache of two mixtures' worth of per-mixture data (`bytes_per_mix`), taken only
+// when it costs no warps and a CTA's contiguous item range (cdiv(n_items, grid)) cannot span more than two mixtures.
+static inline bool plan_stream_cached(const bss_handle* h, const TileGeom& g, int stages, size_t scratch_per_warp, long long n_items,
+                                      int max_wpc, size_t bytes_per_mix, long long items_per_mix, StreamPlan* out, uint32_t* cache_off,
+                                      size_t* smem_bytes) {
+    StreamPlan full;
+    const size_t cache_bytes = 2 * bytes_per_mix;
+    if (!plan_stream(h, g, stages, scratch_per_warp, n_items, max_wpc, &full)) return false;
+    if (!plan_stream(h, g, stages, scratch_per_warp, n_items, max_wpc, out, cache_bytes + 16)) return false;
+    if (out->wpc != full.wpc || out->grid != full.grid) return false;
+    if (cdiv(n_items, out->grid) > items_per_mix) return false;
+    *cache_off = (uint32_t)round_up((int)out->smem_bytes, 16);
+    *smem_bytes = *cache_off + cache_bytes;
     return true;
 }
 

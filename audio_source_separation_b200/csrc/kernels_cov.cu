@@ -25,6 +25,7 @@ struct CovParams {
     int n_groups;
     double inv_T;
     uint32_t scratch_off, scratch_stride, ring_off;
+    uint32_t cache_off;  // CACHE: shared-memory copy of the activation rows of the (at most two) mixtures a CTA touches
 };
 
 // Pair layout of one Hermitian accumulator: DP = ceil(C/2) diagonal pairs (d0,d1), (d2,d3), ...
@@ -65,7 +66,10 @@ __device__ __forceinline__ void accumulate_frame(float2 (&acc)[NS][Pairs<C>::NP]
 }
 
 // KT > 0: n_basis known at compile time (basis row in registers); KT == 0: run-time K, basis row in smem.
-template <int C, int NS, int WM, int KT, bool POW>
+// CACHE: every CTA owns a contiguous range of at most F bins, i.e. at most two mixtures; their activation rows
+// (N K Tp floats each, shared by all bins of a mixture) are copied to shared memory once, so the weight
+// computation reads LDS instead of L2-latency LDG (the loads it replaces cost 30% of the kernel time).
+template <int C, int NS, int WM, int KT, bool POW, bool CACHE>
 __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,12 +83,17 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
     constexpr int CC = C * C;
 
     float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);
-    WarpStream<COV_STAGES> st;
-    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * COV_STAGES,
-             smem + p.ring_off + (size_t)warp * COV_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
-             (int)(gridDim.x * wpc), (int)p.n_items, p.n_groups, lane);
     const int Tp = a.Tp;
     const int K = KT > 0 ? KT : a.K;
+    // a CTA walks the contiguous item range [lo, hi); its warps interleave inside it
+    int lo, hi;
+    cta_item_range((int)p.n_items, lo, hi);
+    WarpStream<COV_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * COV_STAGES,
+             smem + p.ring_off + (size_t)warp * COV_STAGES * p.g.stage_bytes, a.X, lo + warp, wpc, hi, p.n_groups, lane);
+    const float* vcache = reinterpret_cast<const float*>(smem + p.cache_off);
+    int b_lo = 0;
+    if (CACHE) b_lo = load_act_cache(reinterpret_cast<float*>(smem + p.cache_off), a.act, a.NW * K * Tp, lo, hi, p.n_groups, a.F);
 
     float2 acc[NS][NP];
 #pragma unroll
@@ -95,12 +104,12 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
     // per-item state
     int b = 0, f = 0, w0 = 0;
     const float* wrow[NS];          // per weight set: activation rows / frame weights / explicit weights of this item
+    int woff[NS];                   // CACHE: float offset of the weight set's activation rows inside vcache
     float tbr[NS][KT > 0 ? KT : 1];
-    bool live[NS];
 
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, a.X, p.n_groups);
         if (st.first_slab()) {
             const int bf = st.cons.item / p.n_groups;
             const int grp = st.cons.item - bf * p.n_groups;
@@ -109,10 +118,11 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
             w0 = grp * NS;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                live[s] = w0 + s < a.n_sel;
-                const int sw = live[s] ? a.wsel[w0 + s] : 0;
+                // weight sets past n_sel reuse set 0: they accumulate values that are never stored
+                const int sw = w0 + s < a.n_sel ? a.wsel[w0 + s] : 0;
                 if (WM == WM_ILRMA) {
                     wrow[s] = a.act + ((size_t)b * a.NW + sw) * K * Tp;
+                    woff[s] = ((b - b_lo) * a.NW + sw) * K * Tp;
                     const float* tsrc = a.basis + (((size_t)b * a.NW + sw) * a.F + f) * K;
                     if (KT > 0) {
 #pragma unroll
@@ -131,11 +141,11 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
             if (WM == WM_ILRMA && KT == 0) __syncwarp();
         }
 
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
 
-#pragma unroll 2
+#pragma unroll 1   // unrolling spills: the 64 accumulator registers leave no room for a second frame pair in flight
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
@@ -145,18 +155,20 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 if (WM == WM_UNIT) {
-                    wa[s] = wb[s] = live[s] ? 1.f : 0.f;
+                    wa[s] = wb[s] = 1.f;
                 } else if (WM == WM_ILRMA) {
                     float2 r = make_float2(0.f, 0.f);
                     if (KT > 0) {
 #pragma unroll
                         for (int k = 0; k < (KT > 0 ? KT : 1); ++k) {
-                            const float2 vv = __ldg(reinterpret_cast<const float2*>(wrow[s] + (size_t)k * Tp + t));
+                            const float2 vv = CACHE ? *reinterpret_cast<const float2*>(vcache + woff[s] + k * Tp + t)
+                                                    : __ldg(reinterpret_cast<const float2*>(wrow[s] + (size_t)k * Tp + t));
                             r = __ffma2_rn(vv, make_float2(tbr[s][k], tbr[s][k]), r);
                         }
                     } else {
                         for (int k = 0; k < K; ++k) {
-                            const float2 vv = __ldg(reinterpret_cast<const float2*>(wrow[s] + (size_t)k * Tp + t));
+                            const float2 vv = CACHE ? *reinterpret_cast<const float2*>(vcache + woff[s] + k * Tp + t)
+                                                    : __ldg(reinterpret_cast<const float2*>(wrow[s] + (size_t)k * Tp + t));
                             const float tk = tb[s * K + k];
                             r = __ffma2_rn(vv, make_float2(tk, tk), r);
                         }
@@ -167,12 +179,12 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
                     }
                     r.x = fmaxf(r.x, a.eps);
                     r.y = fmaxf(r.y, a.eps);
-                    wa[s] = live[s] ? rcp_fast(r.x) : 0.f;
-                    wb[s] = live[s] ? rcp_fast(r.y) : 0.f;
+                    wa[s] = rcp_fast(r.x);
+                    wb[s] = rcp_fast(r.y);
                 } else {
                     const float2 vv = __ldg(reinterpret_cast<const float2*>(wrow[s] + t));
-                    wa[s] = live[s] ? vv.x : 0.f;
-                    wb[s] = live[s] ? vv.y : 0.f;
+                    wa[s] = vv.x;
+                    wb[s] = vv.y;
                 }
             }
             float2 x0[C], x1[C];
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
             accumulate_frame<C, NS>(acc, x1, wb);
         }
 
-        if (st.last_slab()) {
+        if (st.last_slab(p.g)) {
             float flat[MP];
 #pragma unroll
             for (int i = 0; i < MP; ++i) flat[i] = 0.f;
@@ -215,8 +227,22 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
                 }
             }
         }
-        st.release();
+        st.release(p.g);
     }
+}
+
+template <int C, int NS, int WM, int KT, bool POW, bool CACHE>
+int launch_cov_c(bss_handle* h, CovParams& p, const StreamPlan& sp, size_t smem_bytes) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(cov_kernel<C, NS, WM, KT, POW, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->max_smem));
+        attr_done = true;
+    }
+    cov_kernel<C, NS, WM, KT, POW, CACHE><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
 }
 
 template <int C, int NS, int WM, int KT, bool POW>
@@ -227,23 +253,24 @@ int launch_cov_t(bss_handle* h, const CovArgs& a) {
     p.n_groups = (a.n_sel + NS - 1) / NS;
     p.n_items = (long long)a.B * a.F * p.n_groups;
     p.inv_T = 1.0 / (double)a.T;
+    p.cache_off = 0;
     if (p.n_items == 0) return BSS_OK;
+    const size_t scratch = (size_t)NS * (a.K > 0 ? a.K : 1) * 4;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, COV_STAGES, (size_t)NS * (a.K > 0 ? a.K : 1) * 4, (int)p.n_items, COV_MAX_WARPS, &sp))
+    size_t smem_bytes = 0;
+    if (WM == WM_ILRMA && plan_stream_cached(h, p.g, COV_STAGES, scratch, p.n_items, COV_MAX_WARPS, (size_t)a.NW * a.K * a.Tp * sizeof(float),
+                                             (long long)a.F * p.n_groups, &sp, &p.cache_off, &smem_bytes)) {
+        p.scratch_off = sp.scratch_off;
+        p.scratch_stride = sp.scratch_stride;
+        p.ring_off = sp.ring_off;
+        return launch_cov_c<C, NS, WM, KT, POW, true>(h, p, sp, smem_bytes);
+    }
+    if (!plan_stream(h, p.g, COV_STAGES, scratch, (int)p.n_items, COV_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "covariance: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
     p.ring_off = sp.ring_off;
-    static bool attr_done = false;
-    if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(cov_kernel<C, NS, WM, KT, POW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         h->max_smem));
-        attr_done = true;
-    }
-    cov_kernel<C, NS, WM, KT, POW><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
-    h->launches++;
-    BSS_CUDA(h, cudaGetLastError());
-    return BSS_OK;
+    return launch_cov_c<C, NS, WM, KT, POW, false>(h, p, sp, sp.smem_bytes);
 }
 
 template <int C, int NS>

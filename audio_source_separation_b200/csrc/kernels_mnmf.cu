@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
     int bf = 0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, a.X, p.per_bin);
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
             k0 = (st.cons.item - bf * p.per_bin) * MN_KC;
@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
             __syncwarp();
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
                         }
                 }
         }
-        if (st.last_slab()) {
+        if (st.last_slab(p.g)) {
             constexpr int MP = MN_NMAX * MN_KC * 2;   // 32
             float flat[MP];
 #pragma unroll
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
                 p.out_f[idx] = a.basis[idx] * sqrtf(mine / dn);
             }
         }
-        st.release();
+        st.release(p.g);
     }
 }
 
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     int bf = 0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, a.X, p.per_bin);
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
             n0 = (st.cons.item - bf * p.per_bin) * MN_NG;
@@ -379,9 +379,9 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
             __syncwarp();
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
                 }
             }
         }
-        if (st.last_slab()) {
+        if (st.last_slab(p.g)) {
             constexpr int MV = MN_NG * M * 2;
             constexpr int MP = (MV + 31) / 32 * 32;
             constexpr int Q = MP / 32;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
             }
             __syncwarp();
         }
-        st.release();
+        st.release(p.g);
     }
 }
 
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
     int b = 0, f = 0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, a.X, 1);
         const int bf = st.cons.item;
         if (st.first_slab()) {
             b = bf / a.F;
@@ -499,9 +499,9 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
             total = 0.0;
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
         float part = 0.f;
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
@@ -523,11 +523,11 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
             }
         }
         total += (double)part;
-        if (st.last_slab()) {
+        if (st.last_slab(p.g)) {
             const double s = warp_sum(total);
             if (lane == 0) p.out_d[bf] = s;
         }
-        st.release();
+        st.release(p.g);
     }
 }
 
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_separate_kernel(const MnParams p)
     float2 qi[M];
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, a.X, 1);
         const int bf = st.cons.item;
         if (st.first_slab()) {
             b = bf / a.F;
@@ -559,9 +559,9 @@ __global__ void __launch_bounds__(256, 1) mnmf_separate_kernel(const MnParams p)
 #pragma unroll
             for (int m = 0; m < M; ++m) qi[m] = __ldg(p.qinv + (size_t)bf * M + m);
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[M];
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_separate_kernel(const MnParams p)
                     if (t + 1 < a.T) o[1] = cf_make(o1.x * lam[n].y, o1.y * lam[n].y);
                 }
         }
-        st.release();
+        st.release(p.g);
     }
 }
 

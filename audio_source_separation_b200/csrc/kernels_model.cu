@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
     cf w[C][C];
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, p.X, 1);
         const int bf = st.cons.item;
         const int b = bf / p.F, f = bf - b * p.F;
         if (st.first_slab()) {
@@ -162,9 +162,9 @@ __global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
                 }
             }
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) separate_kernel(const SepParams p) {
                 }
             }
         }
-        st.release();
+        st.release(p.g);
     }
 }
 
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
     double total = 0.0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, (FROM_Y ? a.Y : a.X), 1);
         const int bf = st.cons.item;
         const int b = (int)(bf / a.F), f = bf - b * a.F;
         if (st.first_slab()) {
@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
             total = 0.0;
             __syncwarp();
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
         float part = 0.f;
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
@@ -293,11 +293,11 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
             }
         }
         total += (double)part;
-        if (st.last_slab()) {
+        if (st.last_slab(p.g)) {
             const double s = warp_sum(total);
             if (lane == 0) p.out[bf] = s;
         }
-        st.release();
+        st.release(p.g);
     }
 }
 

@@ -4,6 +4,9 @@
 // The estimates Y = W X are never stored: their power is recomputed from the staged bin tile.
 // Arithmetic is paired fp32 (FFMA2): a complex multiply-add is two instructions and the two frames a
 // lane handles per step share every weight computation.
+#include <algorithm>
+#include <cmath>
+
 #include "handle.h"
 
 namespace {
@@ -79,11 +82,13 @@ struct MuParams {
     long long n_items;
     int n_kc;
     uint32_t scratch_off, scratch_stride, ring_off;
+    uint32_t cache_off;   // CACHE: shared-memory copy of the activation rows of the mixtures this CTA touches
 };
 
 // KFIX: n_basis == KC at compile time (basis row in registers, one item per bin);
 // otherwise n_basis is a run-time value, an item is a (bin, chunk of KC basis vectors) pair.
-template <int C, int KC, bool KFIX, bool FROM_Y>
+// CACHE: CTA-contiguous bin ranges with the activation rows in shared memory (see cov_kernel).
+template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE>
 __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const MuParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,10 +103,15 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
 
     float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);   // [N][K] (run-time K only)
     float* red = tb + (KFIX ? 0 : N * K);                                                           // [MP]
+    int lo, hi;
+    cta_item_range((int)p.n_items, lo, hi);
     WarpStream<MU_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
-             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
-             (int)(blockIdx.x * wpc + warp), (int)(gridDim.x * wpc), (int)p.n_items, p.n_kc, lane);
+             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X, lo + warp, wpc, hi, p.n_kc, lane);
+    const float* vcache = reinterpret_cast<const float*>(smem + p.cache_off);
+    int b_lo = 0;
+    if (CACHE) b_lo = load_act_cache(reinterpret_cast<float*>(smem + p.cache_off), a.act, N * K * Tp, lo, hi, p.n_kc, a.F);
+    int voff = 0;
 
     float2 num[N][KC], den[N][KC];
 #pragma unroll
@@ -115,13 +125,14 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
 
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, (FROM_Y ? a.Y : a.X), p.n_kc);
         if (st.first_slab()) {
             const int bf = st.cons.item / p.n_kc;
             k0 = (st.cons.item - bf * p.n_kc) * KC;
             b = bf / a.F;
             f = bf - b * a.F;
             vrow = a.act + (size_t)b * N * K * Tp;
+            voff = (b - b_lo) * N * K * Tp;
             if (KFIX) {
 #pragma unroll
                 for (int n = 0; n < N; ++n)
@@ -137,10 +148,10 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
             load_filter<C, FROM_Y>(w, a.Wf + (size_t)bf * C * C);
         }
 
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
-#pragma unroll 2
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
+#pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
 #pragma unroll
@@ -150,20 +161,20 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
             const int t = tbase + tt;
 #pragma unroll
             for (int n = 0; n < N; ++n) {
-                const float* v = vrow + (size_t)n * K * Tp + t;
+                const float* v = CACHE ? vcache + voff + n * K * Tp + t : vrow + (size_t)n * K * Tp + t;
                 float2 tv = make_float2(0.f, 0.f);
                 float2 vk[KC];
                 if (KFIX) {
 #pragma unroll
                     for (int kk = 0; kk < KC; ++kk) {
-                        vk[kk] = __ldg(reinterpret_cast<const float2*>(v + (size_t)kk * Tp));
+                        vk[kk] = CACHE ? *reinterpret_cast<const float2*>(v + kk * Tp) : __ldg(reinterpret_cast<const float2*>(v + (size_t)kk * Tp));
                         tv = __ffma2_rn(vk[kk], make_float2(tk[n][kk], tk[n][kk]), tv);
                     }
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < KC; ++kk) vk[kk] = make_float2(0.f, 0.f);
                     for (int k = 0; k < K; ++k) {
-                        const float2 vv = __ldg(reinterpret_cast<const float2*>(v + (size_t)k * Tp));
+                        const float2 vv = CACHE ? *reinterpret_cast<const float2*>(v + k * Tp) : __ldg(reinterpret_cast<const float2*>(v + (size_t)k * Tp));
                         const float tkv = tb[n * K + k];
                         tv = __ffma2_rn(vv, make_float2(tkv, tkv), tv);
 #pragma unroll
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
             }
         }
 
-        if (st.last_slab()) {
+        if (st.last_slab(p.g)) {
             float flat[MP];
 #pragma unroll
             for (int i = 0; i < MP; ++i) flat[i] = 0.f;
@@ -216,8 +227,22 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
                 }
             }
         }
-        st.release();
+        st.release(p.g);
     }
+}
+
+template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE>
+int launch_mu_basis_c(bss_handle* h, const MuParams& p, const StreamPlan& sp, size_t smem_bytes) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->max_smem));
+        attr_done = true;
+    }
+    mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
 }
 
 template <int C, int KC, bool KFIX, bool FROM_Y>
@@ -227,23 +252,20 @@ int launch_mu_basis_t(bss_handle* h, const MuArgs& a) {
     p.g = make_tile_geom(C, a.Tp, MU_SLAB);
     p.n_kc = KFIX ? 1 : (a.K + KC - 1) / KC;
     p.n_items = (long long)a.B * a.F * p.n_kc;
+    p.cache_off = 0;
     constexpr int MP = (C * KC * 2 + 31) / 32 * 32;
+    const size_t scratch = ((KFIX ? 0 : (size_t)C * a.K) + MP) * 4;   // [N][K] basis row (run-time K only) + reduction buffer
     StreamPlan sp;
-    if (!plan_stream(h, p.g, MU_STAGES, ((size_t)C * a.K + MP) * 4, (int)p.n_items, MU_MAX_WARPS, &sp))
+    size_t smem_bytes = 0;
+    const bool cached = plan_stream_cached(h, p.g, MU_STAGES, scratch, p.n_items, MU_MAX_WARPS, (size_t)C * a.K * a.Tp * sizeof(float),
+                                           (long long)a.F * p.n_kc, &sp, &p.cache_off, &smem_bytes);
+    if (!cached && !plan_stream(h, p.g, MU_STAGES, scratch, p.n_items, MU_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "source model: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
     p.ring_off = sp.ring_off;
-    static bool attr_done = false;
-    if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, KFIX, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         h->max_smem));
-        attr_done = true;
-    }
-    mu_basis_kernel<C, KC, KFIX, FROM_Y><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
-    h->launches++;
-    BSS_CUDA(h, cudaGetLastError());
-    return BSS_OK;
+    if (cached) return launch_mu_basis_c<C, KC, KFIX, FROM_Y, true>(h, p, sp, smem_bytes);
+    return launch_mu_basis_c<C, KC, KFIX, FROM_Y, false>(h, p, sp, sp.smem_bytes);
 }
 
 // ------------------------------------------------------------------------------------------- activation
@@ -390,9 +412,280 @@ __global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, cons
     act[idx] = act[idx] * pow_q(num / den, a.q_exp);
 }
 
+// ---- streamed stage 1 (n_basis fixed at compile time) ------------------------------------------------------
+// A warp owns ONE 128-frame block index s of one chunk of bins and streams that block of every bin of the chunk
+// through a private ring: each stage holds the block (one bulk copy, 4 KB at C = 4) followed by the bin's packed
+// parameters (demixing filter rows and basis values, one more bulk copy), so the loop body touches only shared
+// memory and registers.  The lane's activation values are loop invariants (registers), as are its accumulators.
+constexpr int ACT_STAGES = 4;
+constexpr int ACT_WARPS = 4;
+
+struct ActParams {
+    MuArgs a;
+    float* part;                  // [B][n_chunks][N][K][2][Tp]
+    const unsigned char* pbin;    // packed per-bin parameters, pb_stride bytes per bin: Wf [C][C] complex64 | T [N][K] float
+    int pb_stride;
+    int n_chunks, bins_per_chunk, n_blocks;
+    int n_items;                  // B * n_chunks * n_blocks
+    uint32_t stage_bytes, par_off;
+};
+
+__global__ void __launch_bounds__(256) pack_bin_params_kernel(const cf* Wf, const float* basis, unsigned char* out, int B, int N,
+                                                              int C, int F, int K, int stride, int with_filter) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int words = stride >> 2;
+    if (idx >= (long long)B * F * words) return;
+    const int w = (int)(idx % words);
+    const long long bf = idx / words;
+    const int f = (int)(bf % F), b = (int)(bf / F);
+    const int nw = with_filter ? C * C * 2 : 0;
+    float v = 0.f;
+    if (w < nw) {
+        v = reinterpret_cast<const float*>(Wf + (size_t)bf * C * C)[w];
+    } else if (w < nw + N * K) {
+        const int i = w - nw, n = i / K, k = i - n * K;
+        v = basis[(((size_t)b * N + n) * F + f) * K + k];
+    }
+    reinterpret_cast<float*>(out)[idx] = v;
+}
+
+template <int C, int KC, bool FROM_Y>
+__global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_stream_kernel(const ActParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const MuArgs& a = p.a;
+    constexpr int N = C;
+    const int item = (int)blockIdx.x * ACT_WARPS + warp;
+    if (item >= p.n_items) return;
+    // item -> (b, chunk, block), block fastest: the warps of a CTA read consecutive 4 KB blocks of the same bins
+    const int s = item % p.n_blocks;
+    const int bc = item / p.n_blocks;
+    const int chunk = bc % p.n_chunks;
+    const int b = bc / p.n_chunks;
+    const int f_begin = chunk * p.bins_per_chunk;
+    const int f_end = min(a.F, f_begin + p.bins_per_chunk);
+    const int Tp = a.Tp;
+    const int blk0 = s * BSS_XSLAB;
+    const int L = min(BSS_XSLAB, Tp - blk0);          // frames of this block (even)
+    const uint32_t blk_bytes = (uint32_t)(C * L * 8);
+    const cf* src0 = (FROM_Y ? a.Y : a.X) + (size_t)b * a.F * C * Tp + (size_t)blk0 * C;
+    const unsigned char* par0 = p.pbin + (size_t)b * a.F * p.pb_stride;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * ACT_STAGES;
+    unsigned char* ring = smem + 128 + (size_t)warp * ACT_STAGES * p.stage_bytes;
+    const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < ACT_STAGES; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    auto issue = [&](int f, int stage) {
+        if (lane == 0) {
+            const uint32_t bar = bars_sa + 8u * (uint32_t)stage;
+            const uint32_t dst = ring_sa + (uint32_t)stage * p.stage_bytes;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(blk_bytes + (uint32_t)p.pb_stride)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src0 + (size_t)f * C * Tp), "r"(blk_bytes), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + p.par_off),
+                         "l"(par0 + (size_t)f * p.pb_stride), "r"((uint32_t)p.pb_stride), "r"(bar)
+                         : "memory");
+        }
+    };
+    int fp = f_begin, pstage = 0;
+#pragma unroll 1
+    for (int i = 0; i < ACT_STAGES - 1 && fp < f_end; ++i, ++fp) {
+        issue(fp, pstage);
+        pstage = pstage + 1 == ACT_STAGES ? 0 : pstage + 1;
+    }
+
+    // loop invariants of this lane: activation values of its frame pairs (two pairs per 128-frame block)
+    float2 vreg[2][N][KC];
+    float2 num[2][N][KC], den[2][N][KC];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int tt = 2 * lane + 64 * j;
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                vreg[j][n][kk] = tt < L ? __ldg(reinterpret_cast<const float2*>(a.act + (((size_t)b * N + n) * KC + kk) * Tp + blk0 + tt))
+                                        : make_float2(0.f, 0.f);
+                num[j][n][kk] = den[j][n][kk] = make_float2(0.f, 0.f);
+            }
+    }
+
+    int cstage = 0;
+    uint32_t cphase = 0;
+#pragma unroll 1
+    for (int f = f_begin; f < f_end; ++f) {
+        if (fp < f_end) {
+            issue(fp, pstage);
+            ++fp;
+            pstage = pstage + 1 == ACT_STAGES ? 0 : pstage + 1;
+        }
+        {
+            const uint32_t bar = bars_sa + 8u * (uint32_t)cstage;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(cphase)
+                    : "memory");
+            }
+        }
+        const unsigned char* stage = ring + (size_t)cstage * p.stage_bytes;
+        const cf* xs = reinterpret_cast<const cf*>(stage);
+        const float2* wf = reinterpret_cast<const float2*>(stage + p.par_off);
+        const float* tb = reinterpret_cast<const float*>(stage + p.par_off) + (FROM_Y ? 0 : C * C * 2);
+        float2 w[C][C];
+        if (!FROM_Y) {
+#pragma unroll
+            for (int n = 0; n < C; ++n)
+#pragma unroll
+                for (int c = 0; c < C; ++c) w[n][c] = wf[n * C + c];
+        }
+        float tk[N][KC];
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) tk[n][kk] = tb[n * KC + kk];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int tt = 2 * lane + 64 * j;
+            if (tt < L) {
+                float4 xv[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * L + tt);
+                float2 P[C];
+                frame_power2<C, FROM_Y>(xv, w, P);
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                    float2 tv = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tk[n][kk], tk[n][kk]), tv);
+                    tv.x = fmaxf(tv.x, a.eps);
+                    tv.y = fmaxf(tv.y, a.eps);
+                    float2 sa, sb;
+                    mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk) {
+                        const float2 t2 = make_float2(tk[n][kk], tk[n][kk]);
+                        num[j][n][kk] = __ffma2_rn(sa, t2, num[j][n][kk]);
+                        den[j][n][kk] = __ffma2_rn(sb, t2, den[j][n][kk]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (++cstage == ACT_STAGES) {
+            cstage = 0;
+            cphase ^= 1u;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int tt = 2 * lane + 64 * j;
+        if (tt < L) {
+#pragma unroll
+            for (int n = 0; n < N; ++n)
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) {
+                    float* dst = p.part + (((((size_t)b * p.n_chunks + chunk) * N + n) * KC + kk) * 2) * Tp + blk0 + tt;
+                    *reinterpret_cast<float2*>(dst) = num[j][n][kk];
+                    *reinterpret_cast<float2*>(dst + Tp) = den[j][n][kk];
+                }
+        }
+    }
+}
+
+// host: choose the number of bin chunks so that the warps fill the machine in whole waves
+template <int C, int KC, bool FROM_Y>
+int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done) {
+    *done = false;
+    ActParams p{};
+    p.a = a;
+    p.n_blocks = (a.Tp + BSS_XSLAB - 1) / BSS_XSLAB;
+    const int blk_frames = a.Tp < BSS_XSLAB ? a.Tp : BSS_XSLAB;
+    p.pb_stride = round_up((FROM_Y ? 0 : C * C * 8) + C * KC * 4, 16);
+    p.par_off = (uint32_t)round_up(C * blk_frames * 8, 16);
+    p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
+    const size_t smem_bytes = 128 + (size_t)ACT_WARPS * ACT_STAGES * p.stage_bytes;
+    if (smem_bytes > (size_t)h->max_smem) return BSS_OK;   // fall back to the direct-load kernel
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_stream_kernel<C, KC, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        attr_done = true;
+    }
+    int ctas_per_sm = 1;
+    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_act_stream_kernel<C, KC, FROM_Y>, ACT_WARPS * 32, smem_bytes));
+    if (ctas_per_sm < 1) return BSS_OK;
+    const long long slots = (long long)h->n_sm * ctas_per_sm * ACT_WARPS;
+    const long long per_chunk = (long long)a.B * p.n_blocks;
+    // candidates: chunks of at least 16 bins, at most 4 waves; keep the most efficient (ties: fewer chunks)
+    int best = 1;
+    double best_eff = -1.0;
+    const int c_max = (int)std::max<long long>(1, std::min<long long>(a.F / 16, cdiv(4 * slots, per_chunk)));
+    for (int c = 1; c <= c_max; ++c) {
+        const double waves = (double)(per_chunk * c) / (double)slots;
+        const double eff = waves / std::ceil(waves);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = c;
+        }
+    }
+    p.bins_per_chunk = (int)cdiv(a.F, best);
+    p.n_chunks = (int)cdiv(a.F, p.bins_per_chunk);
+    const long long n_items = per_chunk * p.n_chunks;
+    if (n_items > 0x7fffffffLL) return BSS_OK;
+    p.n_items = (int)n_items;
+    const size_t need = (size_t)a.B * p.n_chunks * C * KC * 2 * a.Tp;
+    if (need > h->part_elems) {
+        if (h->part) cudaFree(h->part);
+        h->part = nullptr;
+        h->part_elems = 0;
+        BSS_CUDA(h, cudaMalloc(&h->part, need * sizeof(float)));
+        h->part_elems = need;
+    }
+    const size_t pb_bytes = (size_t)a.B * a.F * p.pb_stride;
+    BSS_TRY(ensure_staging(h, pb_bytes));
+    p.pbin = (const unsigned char*)h->staging;
+    p.part = h->part;
+    const long long words = (long long)a.B * a.F * (p.pb_stride >> 2);
+    pack_bin_params_kernel<<<(unsigned)cdiv(words, 256), 256, 0, h->stream>>>(a.Wf, a.basis, (unsigned char*)h->staging, a.B, C, C, a.F,
+                                                                             KC, p.pb_stride, FROM_Y ? 0 : 1);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    mu_act_stream_kernel<C, KC, FROM_Y><<<(unsigned)cdiv(n_items, ACT_WARPS), ACT_WARPS * 32, smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    if (n_chunks_out) *n_chunks_out = p.n_chunks;
+    *done = true;
+    return BSS_OK;
+}
+
 // act == nullptr: stage 1 only (the partial sums stay in h->part, *n_chunks_out tells how many)
 template <int C, int KC, bool KFIX, bool FROM_Y>
 int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_out) {
+    if constexpr (KFIX) {
+        bool done = false;
+        int n_chunks_s = 0;
+        BSS_TRY((launch_mu_act_stream<C, KC, FROM_Y>(h, a, &n_chunks_s, &done)));
+        if (done) {
+            if (n_chunks_out) *n_chunks_out = n_chunks_s;
+            if (!act) return BSS_OK;
+            const long long total = (long long)a.B * C * a.K * a.Tp;
+            mu_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, act, C, n_chunks_s);
+            h->launches++;
+            BSS_CUDA(h, cudaGetLastError());
+            return BSS_OK;
+        }
+    }
     const int n_kc = KFIX ? 1 : (a.K + KC - 1) / KC;
     const int n_slabs = (a.Tp + 63) / 64;
     // enough warps to fill the machine a few times over, but chunks of at least 4 bins

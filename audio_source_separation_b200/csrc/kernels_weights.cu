@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) t_weights_kernel(const TwParams p) {
              (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next();
+        st.issue_next(p.g, p.X, 1);
         const int bf = st.cons.item;
         const int b = bf / p.F, f = bf - b * p.F;
         if (st.first_slab()) {
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(256) t_weights_kernel(const TwParams p) {
             }
             __syncwarp();
         }
-        const cf* xs = st.acquire();
-        const int nf = st.frames();
-        const int tbase = st.frame0();
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
             float4 xv[C];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) t_weights_kernel(const TwParams p) {
                 *reinterpret_cast<float2*>(p.iw + ((size_t)bf * N + n) * p.Tp + t) = make_float2(1.f / x0, 1.f / x1);
             }
         }
-        st.release();
+        st.release(p.g);
     }
 }
 
