@@ -36,7 +36,7 @@ class Config(ctypes.Structure):
         ('partitioning', ctypes.c_int32), ('algorithm', ctypes.c_int32), ('n_batch', ctypes.c_int32),
         ('n_channels', ctypes.c_int32), ('n_sources', ctypes.c_int32), ('n_bins', ctypes.c_int32),
         ('n_frames', ctypes.c_int32), ('n_basis', ctypes.c_int32), ('reference_id', ctypes.c_int32),
-        ('device', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('device', ctypes.c_int32), ('stream_priority', ctypes.c_int32),
         ('domain', ctypes.c_double), ('nu', ctypes.c_double), ('eps', ctypes.c_double), ('threshold', ctypes.c_double),
     ]
 
@@ -128,7 +128,7 @@ class Handle:
         c = Config()
         defaults = dict(method=GAUSS_ILRMA, spatial=SPATIAL_IP, normalize=NORMALIZE_POWER, partitioning=0, algorithm=ALG_MM,
                         n_batch=1, n_channels=0, n_sources=0, n_bins=0, n_frames=0, n_basis=1, reference_id=0, device=0,
-                        reserved=0, domain=2.0, nu=1.0, eps=1e-12, threshold=1e12)
+                        stream_priority=0, domain=2.0, nu=1.0, eps=1e-12, threshold=1e12)
         defaults.update(cfg)
         for k, v in defaults.items():
             setattr(c, k, v)

@@ -70,6 +70,59 @@ class BatchedGaussILRMA:
         B, C, F, T = X.shape
         return h.separate((B, C, F, T), dtype, projection_back=True)
 
+    def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline=4):
+        """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
+        `out` (B,N,F,T) complex64 (allocated when None).  The batch is cut into `pipeline` sub-batches, each with its own
+        handle and CUDA stream and driven by its own host thread, so the host->device copy of one sub-batch and the
+        device->host copy of another overlap the update loop of the rest (pass pinned arrays to make the copies
+        asynchronous).  Mixtures are independent, so the result is identical to one undivided call."""
+        from concurrent.futures import ThreadPoolExecutor
+        B, C, F, T = X.shape
+        K = self.n_basis
+        if out is None:
+            out = np.empty((B, C, F, T), dtype=np.complex64)
+        assert out.shape == (B, C, F, T) and out.dtype == np.complex64 and out.flags.c_contiguous
+        X = X if X.flags.c_contiguous and X.dtype in (np.complex64, np.complex128) else np.ascontiguousarray(X, np.complex128)
+        if basis is None:
+            basis = np.random.rand(B, C, F, K)
+        if activation is None:
+            activation = np.random.rand(B, C, K, T)
+        n_parts = max(1, min(int(pipeline), B))
+        spans = [shard_range(B, i, n_parts) for i in range(n_parts)]
+        if not hasattr(self, '_parts') or len(self._parts) != n_parts:
+            self._parts = [None] * n_parts
+        x_dtype = _lib.C64 if X.dtype == np.complex64 else _lib.C128
+
+        def job(i):
+            lo, hi = spans[i]
+            key = (hi - lo, C, F, T)
+            slot = self._parts[i]
+            if slot is None or slot[0] != key:
+                if slot is not None:
+                    slot[1].close()
+                h = _lib.Handle(method=_lib.GAUSS_ILRMA, spatial=parse_spatial(self.algorithm_spatial),
+                                normalize=parse_normalize(self.normalize), n_batch=hi - lo, n_channels=C, n_sources=C, n_bins=F,
+                                n_frames=T, n_basis=K, reference_id=self.reference_id, device=self.device,
+                                domain=float(self.domain), eps=float(self.eps), threshold=float(self.threshold),
+                                stream_priority=-(n_parts - 1 - i))   # earlier sub-batches finish first: their D2H overlaps the rest
+                self._parts[i] = slot = (key, h)
+            h = slot[1]
+            # small uploads first: queued behind the other sub-batches' input copies they would wait for all of them
+            h.reset_spatial()
+            h.set_state(_lib.STATE_BASIS, basis[lo:hi], np.float64)
+            h.set_state(_lib.STATE_ACTIVATION, activation[lo:hi], np.float64)
+            h.set_input_ptr(X[lo:hi].ctypes.data, x_dtype)
+            h.run(iteration)
+            h.separate_into(out[lo:hi].ctypes.data, _lib.C64, projection_back=True)
+            return h.launch_count()
+
+        if n_parts == 1:
+            job(0)
+        else:
+            with ThreadPoolExecutor(max_workers=n_parts) as pool:
+                list(pool.map(job, range(n_parts)))
+        return out
+
     def update_once(self):
         self.handle.update_once()
 

@@ -136,7 +136,14 @@ int bss_create(const bss_config* cfg, bss_handle** out) {
     }
     h->n_sm = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;   // numerically: greatest priority <= least priority
+        CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        int prio = cfg->stream_priority;
+        if (prio < greatest) prio = greatest;
+        if (prio > least) prio = least;
+        CREATE_CUDA(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio));
+    }
     h->stream = h->own_stream;
     CREATE_CUDA(cudaEventCreate(&h->ev0));
     CREATE_CUDA(cudaEventCreate(&h->ev1));
@@ -219,6 +226,8 @@ int bss_set_input(bss_handle* h, const void* x, int dtype) {
     BSS_TRY(launch_covariance(h, ca));
     h->has_input = true;
     h->y_valid = false;
+    // ISS carries estimates instead of a filter: (re)derive them when the filter came first
+    if (h->cfg.spatial == BSS_SPATIAL_ISS && h->cfg.method != BSS_FAST_MNMF && h->has_filter) BSS_TRY(bss_refresh_estimates(h));
     // the caller's buffer may be reused as soon as we return
     BSS_CUDA(h, cudaStreamSynchronize(h->stream));
     return BSS_OK;

@@ -69,6 +69,212 @@ __global__ void __launch_bounds__(64) ip_sweep_kernel(const IpArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------- cooperative sweep
+// The same sweep with G = 2 / 4 / 8 lanes per bin: lane j of a group owns column j of U_n, of A = W U_n and of
+// the inverse being built, all in registers; W sits in shared memory; pivot rows and eliminators travel by
+// width-G shuffles.  The operations and their order are those of mat_inverse / ip_row (smallmat.cuh), so the
+// results agree with the one-thread-per-bin form to rounding -- but a bin costs 1/G of the serial
+// latency and needs no local memory (the serial 8 x 8 form spilled 17 KB per thread).
+__device__ __forceinline__ cd shfl_cd(cd v, int src, int width) {
+    return cd_make(__shfl_sync(BSS_FULL, v.x, src, width), __shfl_sync(BSS_FULL, v.y, src, width));
+}
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(BSS_FULL, v, o, G);
+    return v;
+}
+
+// column j of a packed Hermitian matrix (C diagonals, then strict lower triangle row-major as (re, im))
+template <int C>
+__device__ __forceinline__ void herm_col(const double* p, int j, cd (&col)[C]) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        if (i == j) {
+            col[i] = cd_make(__ldg(p + i), 0.0);
+        } else {
+            const int hi = i > j ? i : j, lo = i > j ? j : i;
+            const int e = C + 2 * (hi * (hi - 1) / 2 + lo);
+            const double re = __ldg(p + e), im = __ldg(p + e + 1);
+            col[i] = cd_make(re, i > j ? im : -im);
+        }
+    }
+}
+
+template <int C>
+__device__ __noinline__ double cond2_of(const cd* A) {
+    Mat<C> M;
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j) M.a[i][j] = A[i * C + j];
+    return mat_cond2(M);
+}
+
+template <int C>
+__global__ void __launch_bounds__(128) ip_sweep_group_kernel(const IpArgs a) {
+    constexpr int G = C <= 2 ? 2 : (C <= 4 ? 4 : 8);
+    constexpr int BPW = 32 / G;                      // bins per warp
+    extern __shared__ __align__(16) unsigned char ip_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, j = lane % G;
+    const bool col_live = j < C;
+    const long long n_bins = (long long)a.B * a.F;
+    long long idx = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * BPW + grp;
+    const bool bin_live = idx < n_bins;
+    if (!bin_live) idx = n_bins - 1;                 // keep the lanes in the shuffles; nothing is written
+    const int b = (int)(idx / a.F), f = (int)(idx - (long long)b * a.F);
+    cd* Ws = reinterpret_cast<cd*>(ip_smem) + (size_t)(warp * BPW + grp) * 2 * C * C;   // W, then a copy of A
+    cd* As = Ws + C * C;
+    for (int e = j; e < C * C; e += G) {
+        const double2 v = a.W[(size_t)idx * C * C + e];
+        Ws[e] = cd_make(v.x, v.y);
+    }
+    __syncwarp();
+    bool singular = false;
+#pragma unroll 1
+    for (int n = 0; n < C; ++n) {
+        cd U[C], A[C], I[C];
+        if (col_live) {
+            herm_col<C>(a.U + (((size_t)b * C + n) * a.F + f) * C * C, j, U);
+        } else {
+#pragma unroll
+            for (int i = 0; i < C; ++i) U[i] = cd_make(0.0, 0.0);
+        }
+        // A[:, j] = W U[:, j]
+        double fa = 0.0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            cd s = cd_make(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < C; ++k) cd_fma(s, Ws[i * C + k], U[k]);
+            A[i] = s;
+            I[i] = cd_make(i == j ? 1.0 : 0.0, 0.0);
+            fa += cd_abs2(s);
+            if (col_live) As[i * C + j] = s;
+        }
+        fa = group_sum<G>(fa);
+        // Gauss-Jordan with partial pivoting, column k owned by lane k
+        bool inv_ok = true;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            int p = k;
+            double best = fabs(A[k].x) + fabs(A[k].y);
+#pragma unroll
+            for (int i = k + 1; i < C; ++i) {
+                const double v = fabs(A[i].x) + fabs(A[i].y);
+                if (v > best) {
+                    best = v;
+                    p = i;
+                }
+            }
+            p = __shfl_sync(BSS_FULL, p, k, G);
+            best = __shfl_sync(BSS_FULL, best, k, G);
+            if (best == 0.0) inv_ok = false;
+#pragma unroll
+            for (int i = k + 1; i < C; ++i) {
+                if (i == p) {
+                    cd t = A[k];
+                    A[k] = A[i];
+                    A[i] = t;
+                    t = I[k];
+                    I[k] = I[i];
+                    I[i] = t;
+                }
+            }
+            const cd piv = cd_div(cd_make(1.0, 0.0), shfl_cd(A[k], k, G));
+            A[k] = A[k] * piv;
+            I[k] = I[k] * piv;
+            cd fct[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) fct[i] = shfl_cd(A[i], k, G);
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                if (i == k) continue;
+                A[i] = A[i] - fct[i] * A[k];
+                I[i] = I[i] - fct[i] * I[k];
+            }
+        }
+        double fi = 0.0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) fi += col_live ? cd_abs2(I[i]) : 0.0;
+        fi = group_sum<G>(fi);
+        // every shuffle below is executed by all 32 lanes: the groups of a warp may disagree on the branches
+        int ok = 0;
+        bool need_svd = false;
+        if (!inv_ok) {
+            singular = true;
+        } else if (!a.use_gate) {
+            ok = 1;
+        } else {
+            // kappa_F / C <= cond_2 <= kappa_F: only the band around the threshold needs the SVD (cond_below)
+            const double kf = sqrt(fa * fi);
+            if (!(kf == kf))
+                ok = 0;
+            else if (kf < a.threshold)
+                ok = 1;
+            else if (kf >= a.threshold * C)
+                ok = 0;
+            else
+                need_svd = true;
+        }
+        if (__any_sync(BSS_FULL, need_svd)) {
+            __syncwarp();
+            double c2 = 0.0;
+            if (need_svd && j == 0) c2 = cond2_of<C>(As);
+            c2 = __shfl_sync(BSS_FULL, c2, 0, G);
+            if (need_svd) ok = c2 < a.threshold ? 1 : 0;
+        }
+        {
+            // w = column n of the inverse, to every lane of the group
+            cd w[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) w[i] = shfl_cd(I[i], n, G);
+            cd wj = w[0];
+#pragma unroll
+            for (int i = 1; i < C; ++i)
+                if (i == j) wj = w[i];
+            // q = w^H U w, lane j contributes (sum_i conj(w_i) U[i][j]) w_j
+            cd s = cd_make(0.0, 0.0);
+#pragma unroll
+            for (int i = 0; i < C; ++i) cd_fma(s, cd_conj(w[i]), U[i]);
+            const cd term = col_live ? s * wj : cd_make(0.0, 0.0);
+            const cd q = cd_make(group_sum<G>(term.x), group_sum<G>(term.y));
+            cd den = cd_sqrt(q);
+            if (a.floor_den && cd_less_real(den, a.eps)) den = cd_make(a.eps, 0.0);
+            __syncwarp();
+            if (inv_ok && ok && col_live) Ws[n * C + j] = cd_div(cd_conj(wj), den);
+        }
+        __syncwarp();
+        if (a.gate && bin_live && j == 0) a.gate[((size_t)b * C + n) * a.F + f] = ok;
+    }
+    if (singular && bin_live && j == 0) atomicAdd(a.flags, 1);
+    if (bin_live) {
+        for (int e = j; e < C * C; e += G) {
+            const cd v = Ws[e];
+            a.W[(size_t)idx * C * C + e] = make_double2(v.x, v.y);
+            if (a.Wf) a.Wf[(size_t)idx * C * C + e] = cf_make((float)v.x, (float)v.y);
+        }
+    }
+    if (a.pw) {
+        // p_n = w_n^H Cx w_n = sum_j (sum_i W[n][i] Cx[i][j]) conj(W[n][j])
+        cd Cx[C];
+        if (col_live) {
+            herm_col<C>(a.Cx + (size_t)idx * C * C, j, Cx);
+        } else {
+#pragma unroll
+            for (int i = 0; i < C; ++i) Cx[i] = cd_make(0.0, 0.0);
+        }
+#pragma unroll 1
+        for (int n = 0; n < C; ++n) {
+            cd s = cd_make(0.0, 0.0);
+#pragma unroll
+            for (int i = 0; i < C; ++i) cd_fma(s, Ws[n * C + i], Cx[i]);
+            const cd t = col_live ? s * cd_conj(Ws[n * C + j]) : cd_make(0.0, 0.0);
+            const double pr = group_sum<G>(t.x);
+            if (bin_live && j == 0) a.pw[((size_t)b * C + n) * a.F + f] = pr;
+        }
+    }
+}
+
 // 2x2 helper for IP2
 struct M2 {
     cd a, b, c, d;   // [[a, b], [c, d]]
@@ -338,10 +544,18 @@ int launch_ip_t(bss_handle* h, const IpArgs& a, int32_t* order_out) {
     const long long n = (long long)a.B * a.F;
     const int threads = 64;
     const unsigned grid = (unsigned)cdiv(n, threads);
-    if (a.pair_m >= 0)
+    if (a.pair_m >= 0) {
         ip2_kernel<C><<<grid, threads, 0, h->stream>>>(a, order_out);
-    else
+    } else if (C <= 4 && n >= 32768) {
+        // plenty of bins: one thread per bin has no shuffle traffic and wins (171 vs 212 us for 64 x 2049 bins, C = 4)
         ip_sweep_kernel<C><<<grid, threads, 0, h->stream>>>(a);
+    } else {
+        constexpr int G = C <= 2 ? 2 : (C <= 4 ? 4 : 8);
+        constexpr int BPW = 32 / G;
+        const int warps = 4;
+        const size_t smem = (size_t)warps * BPW * 2 * C * C * sizeof(cd);
+        ip_sweep_group_kernel<C><<<(unsigned)cdiv(n, (long long)warps * BPW), warps * 32, smem, h->stream>>>(a);
+    }
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;

@@ -348,7 +348,9 @@ __global__ void __launch_bounds__(256) mnmf_act_finish_kernel(const MnArgs a, co
 }
 
 // ------------------------------------------------------------------------------------------- spatial g
-// item = (bin, group of MN_NG sources):  g[n,f,m] *= sqrt(sum_t Lambda x~/R^2 / max(sum_t Lambda/R, eps))
+// item = (bin, group of MN_MG channels):  g[n,f,m] *= sqrt(sum_t Lambda x~/R^2 / max(sum_t Lambda/R, eps)).
+// Grouping by channel (not by source) keeps the per-item front end small: only MN_MG rows of Q x and of R are needed.
+constexpr int MN_MG = 2;
 template <int M>
 __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -361,19 +363,19 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
              smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
              (int)(gridDim.x * wpc), (int)p.n_items, p.per_bin, lane);
-    float2 A[MN_NG][M], Bq[MN_NG][M];
+    float2 A[MN_NMAX][MN_MG], Bq[MN_NMAX][MN_MG];
 #pragma unroll
-    for (int j = 0; j < MN_NG; ++j)
+    for (int n = 0; n < MN_NMAX; ++n)
 #pragma unroll
-        for (int m = 0; m < M; ++m) A[j][m] = Bq[j][m] = make_float2(0.f, 0.f);
-    int b = 0, f = 0, n0 = 0;
+        for (int j = 0; j < MN_MG; ++j) A[n][j] = Bq[n][j] = make_float2(0.f, 0.f);
+    int b = 0, f = 0, m0 = 0;
     int bf = 0;
 #pragma unroll 1
     while (st.active()) {
         st.issue_next(p.g, a.X, p.per_bin);
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
-            n0 = (st.cons.item - bf * p.per_bin) * MN_NG;
+            m0 = (st.cons.item - bf * p.per_bin) * MN_MG;
             b = bf / a.F;
             f = bf - b * a.F;
             __syncwarp();
@@ -387,62 +389,66 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
             float4 xv[M];
 #pragma unroll
             for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
-            float2 xt[M];
-            mn_power<M>(xv, Qs, xt);
             const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
             float2 lam[MN_NMAX];
             mn_lambda(a, tb, hrow, lam);
-            float2 R[M];
-            mn_variance<M>(a, gs, lam, R);
-            float2 u[M], ri[M];
+            float2 u[MN_MG], ri[MN_MG];
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                ri[m] = rcp2n(floor2(R[m], a.eps));
-                u[m] = __fmul2_rn(xt[m], __fmul2_rn(ri[m], ri[m]));
-            }
+            for (int j = 0; j < MN_MG; ++j) {
+                const int m = min(m0 + j, M - 1);
+                float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < MN_NG; ++j) {
-                // Lambda of source n0 + j (compile-time indexed select keeps lam[] in registers)
-                float2 l = make_float2(0.f, 0.f);
+                for (int c = 0; c < M; ++c) {
+                    const float2 w = reinterpret_cast<const float2*>(Qs)[m * M + c];
+                    const float2 x0 = make_float2(xv[c].x, xv[c].y), x1 = make_float2(xv[c].z, xv[c].w);
+                    const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
+                    y0 = __ffma2_rn(x0, wx, y0);
+                    y0 = __ffma2_rn(make_float2(-x0.y, x0.x), wy, y0);
+                    y1 = __ffma2_rn(x1, wx, y1);
+                    y1 = __ffma2_rn(make_float2(-x1.y, x1.x), wy, y1);
+                }
+                const float2 s0 = __fmul2_rn(y0, y0), s1 = __fmul2_rn(y1, y1);
+                const float2 xt = make_float2(s0.x + s0.y, s1.x + s1.y);
+                float2 r = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int n = 0; n < MN_NMAX; ++n)
-                    if (n == n0 + j) l = lam[n];
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    A[j][m] = __ffma2_rn(l, u[m], A[j][m]);
-                    Bq[j][m] = __ffma2_rn(l, ri[m], Bq[j][m]);
-                }
+                    if (n < a.N) {
+                        const float g = gs[n * M + m];
+                        r = __ffma2_rn(lam[n], make_float2(g, g), r);
+                    }
+                ri[j] = rcp2n(floor2(r, a.eps));
+                u[j] = __fmul2_rn(xt, __fmul2_rn(ri[j], ri[j]));
             }
+#pragma unroll
+            for (int n = 0; n < MN_NMAX; ++n)
+#pragma unroll
+                for (int j = 0; j < MN_MG; ++j) {
+                    A[n][j] = __ffma2_rn(lam[n], u[j], A[n][j]);
+                    Bq[n][j] = __ffma2_rn(lam[n], ri[j], Bq[n][j]);
+                }
         }
         if (st.last_slab(p.g)) {
-            constexpr int MV = MN_NG * M * 2;
-            constexpr int MP = (MV + 31) / 32 * 32;
-            constexpr int Q = MP / 32;
+            constexpr int MP = MN_NMAX * MN_MG * 2;   // 32
+            static_assert(MP == 32, "one value per lane");
             float flat[MP];
 #pragma unroll
-            for (int i = 0; i < MP; ++i) flat[i] = 0.f;
+            for (int n = 0; n < MN_NMAX; ++n)
 #pragma unroll
-            for (int j = 0; j < MN_NG; ++j)
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    flat[(j * M + m) * 2] = A[j][m].x + A[j][m].y;
-                    flat[(j * M + m) * 2 + 1] = Bq[j][m].x + Bq[j][m].y;
-                    A[j][m] = Bq[j][m] = make_float2(0.f, 0.f);
+                for (int j = 0; j < MN_MG; ++j) {
+                    flat[(n * MN_MG + j) * 2] = A[n][j].x + A[n][j].y;
+                    flat[(n * MN_MG + j) * 2 + 1] = Bq[n][j].x + Bq[n][j].y;
+                    A[n][j] = Bq[n][j] = make_float2(0.f, 0.f);
                 }
             warp_reduce_scatter<MP>(flat, lane);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) red[Q * lane + q] = flat[q];
-            __syncwarp();
-            for (int i = lane; i < MN_NG * M; i += 32) {
-                const int j = i / M, m = i - j * M, n = n0 + j;
-                if (n < a.N) {
-                    const float av = red[2 * i];
-                    const float bv = fmaxf(red[2 * i + 1], a.eps);
-                    const size_t idx = (((size_t)b * a.N + n) * a.F + f) * M + m;
-                    p.out_f[idx] = a.G[idx] * sqrtf(av / bv);
-                }
+            // lane L holds element L: (n, j, which) = (L / 4, (L / 2) % 2, L % 2)
+            const float mine = flat[0];
+            const float other = __shfl_down_sync(BSS_FULL, mine, 1);
+            const int n = lane / (2 * MN_MG), m = m0 + ((lane >> 1) % MN_MG);
+            if ((lane & 1) == 0 && n < a.N && m < M) {
+                const float bv = fmaxf(other, a.eps);
+                const size_t idx = (((size_t)b * a.N + n) * a.F + f) * M + m;
+                p.out_f[idx] = a.G[idx] * sqrtf(mine / bv);
             }
-            __syncwarp();
         }
         st.release(p.g);
     }
@@ -775,7 +781,7 @@ int mn_update_scm(bss_handle* h) {
     MnParams p{};
     p.a = mn_args(h);
     p.out_f = h->G2;
-    BSS_TRY((launch_stream<M>(h, mnmf_scm_kernel<M>, p, (int)cdiv(h->N, MN_NG), MN_SLAB, 8)));
+    BSS_TRY((launch_stream<M>(h, mnmf_scm_kernel<M>, p, (int)cdiv(M, MN_MG), MN_SLAB, 8)));
     float* t = h->G;
     h->G = h->G2;
     h->G2 = t;

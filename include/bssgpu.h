@@ -114,7 +114,7 @@ typedef struct bss_config {
     int32_t n_basis;       /* K                                                 */
     int32_t reference_id;  /* reference microphone of projection back           */
     int32_t device;        /* CUDA device ordinal                               */
-    int32_t reserved;
+    int32_t stream_priority; /* priority of the handle's own CUDA stream: 0 = default, negative = more urgent (clamped) */
     double domain;         /* 1 <= domain <= 2                                  */
     double nu;             /* degrees of freedom (tILRMA, tNMF)                 */
     double eps;            /* EPS = 1e-12        src/bss/ilrma.py:8             */
