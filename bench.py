@@ -265,6 +265,14 @@ def run_gpu_arm(args):
     peak, peak_src = measured_hbm_peak()
     achieved = cov_bytes / (cov_ms * 1e-3) / 1e9
     step_bytes = B * (3 * 8 * C * F * T)
+    traffic = None   # DRAM bytes of one launch from the committed ncu --set full capture (same workload only)
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'cov_kernel_traffic.json')) as fh:
+            tr = json.load(fh)
+        if tr.get('batch_per_gpu') == B:
+            traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+    except Exception:
+        traffic = None
     loss = h.loss()
     if not np.all(np.isfinite(loss)):
         raise RuntimeError("non-finite loss after the timed loop")
@@ -332,7 +340,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": x_host.numel() * 8 / steps,
                     "d2h_bytes_per_step": y_host.numel() * 8 / steps, "seconds": e2e_s},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "cov_kernel<C=4,NS=4,WM_ILRMA,K=2,CACHE>", "launch_ms": cov_ms, "algorithmic_bytes": cov_bytes,
                          "peak_source": peak_src},
             "roofline_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / steps * 1e-3) / 1e9, "unit": "GB/s",
