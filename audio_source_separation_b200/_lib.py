@@ -50,6 +50,11 @@ SIGNATURES = {
     'bss_set_stream': (_i, [_vp, _vp]),
     'bss_synchronize': (_i, [_vp]),
     'bss_set_input': (_i, [_vp, _vp, _i]),
+    'bss_set_input_waveform': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'bss_stft_frames': (_i, [_i, _i, _i]),
+    'bss_istft_length': (_i, [_i, _i, _i]),
+    'bss_stft': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'bss_istft': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'bss_set_state': (_i, [_vp, _i, _vp, _i]),
     'bss_get_state': (_i, [_vp, _i, _vp, _i]),
     'bss_reset_spatial': (_i, [_vp]),
@@ -174,6 +179,13 @@ class Handle:
             x = as_host(x, np.complex64)
         self._check(self._lib.bss_set_input(self._h, _ptr(x), _DTYPES[x.dtype]))
 
+    def set_input_waveform(self, x, fft_size, hop_size, window):
+        """x (B,C,n_samples) float32/float64 on the host; the STFT runs on the device."""
+        x = as_host(x, np.float32 if x.dtype == np.float32 else np.float64)
+        window = as_host(window, np.float64)
+        self._check(self._lib.bss_set_input_waveform(self._h, _ptr(x), _DTYPES[x.dtype], x.shape[-1], int(fft_size), int(hop_size),
+                                                     _ptr(window)))
+
     def set_input_ptr(self, ptr, dtype):
         """Input already sitting in (pinned) host memory at address `ptr`."""
         self._check(self._lib.bss_set_input(self._h, ctypes.c_void_p(ptr), dtype))
@@ -291,3 +303,42 @@ def demix(x, w, device=0):
     code = lib.bss_demix(device, C, F, T, 0, _ptr(x), _ptr(w), _ptr(y))
     check_static(code, 'bss_demix')
     return y
+
+
+def stft_frames(n_samples, fft_size, hop_size):
+    n = load().bss_stft_frames(int(n_samples), int(fft_size), int(hop_size))
+    if n < 0:
+        _raise(n, "invalid STFT geometry")
+    return n
+
+
+def stft(x, fft_size, hop_size, window, device=0):
+    """x (..., n_samples) real -> (..., fft_size // 2 + 1, n_frames) complex128 (scipy.signal.stft semantics)."""
+    lib = load()
+    x = np.asarray(x)
+    lead = x.shape[:-1]
+    x2 = as_host(x.reshape(-1, x.shape[-1]), np.float64)
+    window = as_host(window, np.float64)
+    n_frames = stft_frames(x2.shape[1], fft_size, hop_size)
+    out = np.empty((x2.shape[0], fft_size // 2 + 1, n_frames), dtype=np.complex128)
+    code = lib.bss_stft(device, x2.shape[0], x2.shape[1], int(fft_size), int(hop_size), _ptr(window), _ptr(x2), _ptr(out))
+    check_static(code, 'bss_stft')
+    return out.reshape(lead + out.shape[1:])
+
+
+def istft(z, fft_size, hop_size, window, device=0):
+    """z (..., fft_size // 2 + 1, n_frames) complex -> (..., n_out) float64 (scipy.signal.istft semantics)."""
+    lib = load()
+    z = np.asarray(z)
+    lead = z.shape[:-2]
+    z2 = as_host(z.reshape((-1,) + z.shape[-2:]), np.complex128)
+    if z2.shape[1] != fft_size // 2 + 1:
+        raise ValueError("expected {} bins, got {}".format(fft_size // 2 + 1, z2.shape[1]))
+    window = as_host(window, np.float64)
+    n_out = lib.bss_istft_length(z2.shape[2], int(fft_size), int(hop_size))
+    if n_out < 1:
+        _raise(EINVAL, "invalid ISTFT geometry")
+    out = np.empty((z2.shape[0], n_out), dtype=np.float64)
+    code = lib.bss_istft(device, z2.shape[0], z2.shape[2], int(fft_size), int(hop_size), _ptr(window), _ptr(z2), _ptr(out))
+    check_static(code, 'bss_istft')
+    return out.reshape(lead + (n_out,))

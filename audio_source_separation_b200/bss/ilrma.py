@@ -325,6 +325,55 @@ class GaussILRMA(ILRMAbase):
         return s.format(**self.__dict__)
 
 
+class ConsistentGaussILRMA(GaussILRMA):
+    """
+    Reference: "Consistent independent low-rank matrix analysis for determined blind source separation"
+    Drop-in for src/bss/ilrma.py:1102-1233.  The reference's update_once first replaces `estimation` by its STFT-consistent
+    projection (:1206-1207), but its IP path then recomputes the estimates from `demix_filter` (:360-364), so the projection
+    never reaches the update ("reference quirks"): what remains is the source model, the IP sweep and
+    a projection-back rescaling of W and T with exponent 2 every iteration (:1219-1233) -- which is what runs here.
+    `fft_size` / `hop_size` are kept as attributes; `transform.stft` provides the GPU STFT/ISTFT pair.
+    """
+
+    def __init__(self, n_basis=10, partitioning=False, algorithm_spatial='IP', reference_id=0, fft_size=None, hop_size=None,
+                 callbacks=None, recordable_loss=True, eps=EPS, threshold=THRESHOLD):
+        super().__init__(n_basis=n_basis, partitioning=partitioning, normalize=False, algorithm_spatial=algorithm_spatial,
+                         reference_id=reference_id, callbacks=callbacks, recordable_loss=recordable_loss, eps=eps,
+                         threshold=threshold)
+
+        if fft_size is None:
+            raise ValueError("Specify `fft_size`.")
+
+        if hop_size is None:
+            hop_size = fft_size // 2
+
+        self.fft_size, self.hop_size = fft_size, hop_size
+
+        assert self.algorithm_spatial == 'IP', "Supports only IP-based spatial update."
+
+    def _config(self):
+        cfg = super()._config()
+        cfg['normalize'] = _lib.NORMALIZE_PROJECTION_BACK   # src/bss/ilrma.py:1219-1226, unconditional
+        cfg['domain'] = 2.0
+        return cfg
+
+    def update_once(self):
+        if self.partitioning:
+            raise NotImplementedError("Not support 'projection-back' based normalization for partitioninig function. Choose 'power' based normalization.")
+        ILRMAbase.update_once(self)
+
+    def __repr__(self):
+        s = "Consistent-GaussILRMA("
+        s += "n_basis={n_basis}"
+        s += ", domain={domain}"
+        s += ", partitioning={partitioning}"
+        s += ", normalize={normalize}"
+        s += ", algorithm_spatial={algorithm_spatial}"
+        s += ")"
+
+        return s.format(**self.__dict__)
+
+
 class tILRMA(ILRMAbase):
     """
     Reference: "Independent low-rank matrix analysis based on complex student's t-distribution for blind audio source separation"

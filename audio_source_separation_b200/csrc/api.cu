@@ -200,6 +200,8 @@ int bss_timer_end(bss_handle* h, float* elapsed_ms) {
     return BSS_OK;
 }
 
+static int finish_input(bss_handle* h);
+
 int bss_set_input(bss_handle* h, const void* x, int dtype) {
     if (!h || !x) return BSS_EINVAL;
     if (is_nmf(h->cfg.method)) return bss_fail(h, BSS_EINVAL, "NMF takes its target through bss_set_state");
@@ -210,6 +212,18 @@ int bss_set_input(bss_handle* h, const void* x, int dtype) {
     BSS_TRY(ensure_staging(h, bytes));
     BSS_CUDA(h, cudaMemcpyAsync(h->staging, x, bytes, cudaMemcpyHostToDevice, h->stream));
     BSS_TRY(launch_import_x(h, h->staging, dtype, h->X, h->B, h->C, h->F, h->T, h->Tp));
+    return finish_input(h);
+}
+
+int bss_set_input_waveform(bss_handle* h, const void* x, int dtype, int n_samples, int fft_size, int hop_size, const double* window) {
+    if (!h || !x || !window) return BSS_EINVAL;
+    if (is_nmf(h->cfg.method)) return bss_fail(h, BSS_EINVAL, "NMF takes its target through bss_set_state");
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    BSS_TRY(stft_into_handle(h, x, dtype, n_samples, fft_size, hop_size, window));
+    return finish_input(h);
+}
+
+static int finish_input(bss_handle* h) {
     // plain covariance mean_t x x^H (algebraic power normalisation / projection back)
     CovArgs ca{};
     ca.X = h->X;

@@ -29,3 +29,6 @@ int mnmf_separate(bss_handle* h, cf* out);
 int nmf_allocate(bss_handle* h);
 int nmf_update_once(bss_handle* h);
 int nmf_loss(bss_handle* h);
+
+// STFT feed: kernels_stft.cu
+int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int fft_size, int hop_size, const double* window);

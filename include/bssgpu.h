@@ -136,6 +136,12 @@ int bss_synchronize(bss_handle* h);
  * Also precomputes the plain spatial covariance mean_t x x^H used by the algebraic forms of
  * power normalisation and projection back. */
 int bss_set_input(bss_handle* h, const void* x, int dtype);
+/* the same from the time-domain mixture: x is (B,C,n_samples) float32/float64 on the host; the STFT of
+ * src/transform/stft.py:4-8 (scipy.signal.stft: zero boundary extension, tail padding, `window`, onesided,
+ * divided by sum(window)) is computed on the device straight into the bin tiles.  The handle must have
+ * n_bins = fft_size/2 + 1 and n_frames = bss_stft_frames(n_samples, fft_size, hop_size); fft_size a power of two. */
+int bss_set_input_waveform(bss_handle* h, const void* x, int dtype, int n_samples, int fft_size, int hop_size,
+                           const double* window);
 /* the state-copy half of Model._reset (src/bss/ilrma.py:67-104) and attribute assignment */
 int bss_set_state(bss_handle* h, int which, const void* src, int dtype);
 /* attribute reads (callbacks, tests) */
@@ -193,6 +199,17 @@ int bss_projection_back_scale(int device, int n_channels, int n_bins, int n_fram
  * x (C,F,T) complex128, w (F,C,C) complex128, y (C,F,T) complex128; `flags` is reserved (0). */
 int bss_demix(int device, int n_channels, int n_bins, int n_frames, int flags, const void* x, const void* w,
               void* y);
+
+/* ---- STFT feed (src/transform/stft.py:4-17 == scipy.signal.stft / istft with window=window_fn) ------------- */
+/* number of frames of stft(x[n_samples]) and length of istft(Z[..., n_frames]) (host arithmetic only) */
+int bss_stft_frames(int n_samples, int fft_size, int hop_size);
+int bss_istft_length(int n_frames, int fft_size, int hop_size);
+/* x (n_signals, n_samples) float64, window (fft_size) float64 -> out (n_signals, fft_size/2+1, n_frames) complex128 */
+int bss_stft(int device, int n_signals, int n_samples, int fft_size, int hop_size, const double* window, const double* x,
+             void* out);
+/* z (n_signals, fft_size/2+1, n_frames) complex128 -> out (n_signals, bss_istft_length(...)) float64 */
+int bss_istft(int device, int n_signals, int n_frames, int fft_size, int hop_size, const double* window, const void* z,
+              double* out);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* CUDA-event timing on the handle's stream: begin/end bracket a region, elapsed in ms */

@@ -175,6 +175,35 @@ def case_nmf(name, kind, F, T, K, iters, domain=2, algorithm='mm', nu=1e3, seed=
          {'Z': Z, 'T0': T0, 'V0': V0}, want)
 
 
+# ------------------------------------------------------------------------------- consistent ILRMA / STFT
+
+def case_consistent_ilrma(name, C, fft_size, hop_size, n_samples, K, iters):
+    """ConsistentGaussILRMA (src/bss/ilrma.py:1102-1233) on the STFT of a random multichannel signal, fed through the
+    reference's own stft wrapper; also pins the stft/istft pair itself (src/transform/stft.py:4-17)."""
+    from bss.ilrma import ConsistentGaussILRMA
+    from transform.stft import stft as ref_stft, istft as ref_istft
+    rng = np.random.default_rng(21)
+    A = np.eye(C) + 0.4 * rng.standard_normal((C, C))
+    s = rng.standard_normal((C, n_samples)) * (0.2 + rng.random((C, 1)))
+    x = (A @ s).astype(np.float32).astype(np.float64)
+    X = ref_stft(x, fft_size=fft_size, hop_size=hop_size)
+    xr = ref_istft(X, fft_size=fft_size, hop_size=hop_size, length=n_samples)
+    F, T = X.shape[1:]
+    Xc = X.astype(np.complex64).astype(np.complex128)
+    W0, T0, V0 = synth.initial_state(C, F, T, K, seed=7)
+    model = ConsistentGaussILRMA(n_basis=K, fft_size=fft_size, hop_size=hop_size)
+    out = model(Xc, iteration=iters, demix_filter=W0, basis=T0, activation=V0)
+    want = {'output': out, 'basis': model.basis, 'activation': model.activation, 'demix_filter': model.demix_filter,
+            'loss': np.array(model.loss)}
+    # the consistency projection never reaches the IP update: the oracle is the projection-back normalised ILRMA
+    o_out, st, o_loss = ilrma.run(Xc, iteration=iters, n_basis=K, spatial='IP', domain=2, normalize_mode='projection-back', W=W0,
+                                  T=T0, V=V0)
+    check(name, {'output': o_out, 'basis': st['T'], 'activation': st['V'], 'demix_filter': st['W'], 'loss': np.array(o_loss)}, want)
+    save(name, dict(model='ConsistentGaussILRMA', n_basis=K, fft_size=fft_size, hop_size=hop_size, iteration=iters,
+                    n_samples=n_samples),
+         {'x': x, 'X': Xc, 'W0': W0, 'T0': T0, 'V0': V0}, dict(want, stft=X, istft=xr))
+
+
 # ------------------------------------------------------------------------------- primitives
 
 def case_primitives():
@@ -250,6 +279,7 @@ def main():
     case_ilrma('ilrma_ip2_power_c2', 2, 17, 40, 2, 'IP2', 'power', 2, 3)
     case_ilrma('ilrma_ip_power_part', 3, 17, 40, 4, 'IP', 'power', 2, 3, partitioning=True)
     case_tilrma('tilrma_nu5', 3, 17, 40, 2, 5.0, 3)
+    case_consistent_ilrma('ilrma_consistent', 2, 64, 16, 1000, 2, 3)
     case_auxiva('auxiva_laplace_ip', 'laplace', 2, 33, 40, 'IP', 4)
     case_auxiva('auxiva_laplace_ip_c4', 'laplace', 4, 17, 40, 'IP', 3)
     case_auxiva('auxiva_gauss_ip', 'gauss', 3, 17, 40, 'IP', 3)

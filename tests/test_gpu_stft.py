@@ -1,0 +1,88 @@
+"""GPU parity of the STFT feed (src/transform/stft.py, i.e. scipy.signal.stft / istft) and of the classes built on it.
+The kernels compute in float32: 2e-6 relative Frobenius error on the spectrogram and on the reconstruction."""
+import numpy as np
+import pytest
+from scipy import signal as ss
+
+from conftest import load_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-6
+
+
+def test_stft_istft_golden(cuda_device):
+    from audio_source_separation_b200.transform.stft import stft, istft
+    meta, i, o = load_golden('ilrma_consistent')
+    n, h = meta['fft_size'], meta['hop_size']
+    Z = stft(i['x'], fft_size=n, hop_size=h)
+    assert Z.shape == o['stft'].shape and Z.dtype == np.complex128
+    assert rel(Z, o['stft']) < TOL
+    y = istft(o['stft'], fft_size=n, hop_size=h, length=meta['n_samples'])
+    assert y.shape == o['istft'].shape
+    assert rel(y, o['istft']) < TOL
+    assert rel(y, i['x']) < TOL          # perfect reconstruction (NOLA holds for hann at 75 % overlap)
+
+
+@pytest.mark.parametrize('n_samples,fft,hop,window', [(66, 8, 2, 'hann'), (1000, 64, 16, 'hamming'), (16000, 1024, 256, 'hann'),
+                                                      (40001, 4096, 2048, 'hann'), (5000, 256, 100, 'hann'), (600, 512, 128, 'hann')])
+def test_stft_matches_scipy(cuda_device, n_samples, fft, hop, window):
+    """The reference's own settings ((4096, 2048) for BSS, (1024, 256) for NMF, the (8, 2) of its _test), a hop that does not
+    divide the frame, a signal barely longer than one frame, odd lengths; batches with leading axes."""
+    from audio_source_separation_b200.transform.stft import stft, istft
+    rng = np.random.default_rng(n_samples)
+    x = rng.standard_normal((2, 3, n_samples))
+    Z = stft(x, fft_size=fft, hop_size=hop, window_fn=window)
+    want = ss.stft(x, nperseg=fft, noverlap=fft - hop, window=window)[2]
+    assert Z.shape == want.shape
+    assert rel(Z, want) < TOL
+    y = istft(want, fft_size=fft, hop_size=hop, window_fn=window)
+    y_want = ss.istft(want, nperseg=fft, noverlap=fft - hop, window=window)[1]
+    assert y.shape == y_want.shape
+    assert rel(y, y_want) < TOL
+
+
+def test_stft_rejects_non_power_of_two(cuda_device):
+    from audio_source_separation_b200.transform.stft import stft
+    with pytest.raises(NotImplementedError):
+        stft(np.zeros(1000), fft_size=1000, hop_size=250)
+
+
+def test_consistent_ilrma_golden(cuda_device):
+    from audio_source_separation_b200.bss.ilrma import ConsistentGaussILRMA
+    meta, i, o = load_golden('ilrma_consistent')
+    model = ConsistentGaussILRMA(n_basis=meta['n_basis'], fft_size=meta['fft_size'], hop_size=meta['hop_size'])
+    out = model(i['X'], iteration=meta['iteration'], demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    assert rel(out, o['output']) < 2e-4
+    assert rel(model.basis, o['basis']) < 2e-4 and rel(model.demix_filter, o['demix_filter']) < 2e-4
+    assert np.max(np.abs(np.array(model.loss) - o['loss']) / np.abs(o['loss'])) < 1e-4
+    with pytest.raises(ValueError):
+        ConsistentGaussILRMA(n_basis=2)
+
+
+def test_waveform_feed_equals_spectrogram_feed(cuda_device):
+    """bss_set_input_waveform: the STFT goes straight into the handle's bin tiles; the update loop must see the same mixture
+    as when the host computes the spectrogram (odd and even frame counts, multi-block tiles)."""
+    from audio_source_separation_b200 import _lib
+    for n_samples, fft, hop in ((4000, 64, 16), (4100, 128, 32)):
+        rng = np.random.default_rng(fft)
+        B, C, K = 2, 3, 2
+        x = rng.standard_normal((B, C, n_samples))
+        X = ss.stft(x, nperseg=fft, noverlap=fft - hop, window='hann')[2]        # (B,C,F,T)
+        F, T = X.shape[2:]
+        assert T > 128
+        T0, V0 = rng.random((B, C, F, K)), rng.random((B, C, K, T))
+        outs = []
+        for feed in ('spectrogram', 'waveform'):
+            h = _lib.Handle(method=_lib.GAUSS_ILRMA, n_batch=B, n_channels=C, n_sources=C, n_bins=F, n_frames=T, n_basis=K)
+            h.reset_spatial()
+            h.set_state(_lib.STATE_BASIS, T0, np.float64)
+            h.set_state(_lib.STATE_ACTIVATION, V0, np.float64)
+            if feed == 'spectrogram':
+                h.set_input(X)
+            else:
+                h.set_input_waveform(x, fft, hop, ss.get_window('hann', fft))
+            h.run(3)
+            outs.append(h.separate((B, C, F, T), np.complex128, projection_back=True))
+            h.close()
+        assert rel(outs[1], outs[0]) < 1e-4

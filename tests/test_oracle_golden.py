@@ -97,3 +97,24 @@ def test_known_answer_losses():
     _, _, loss = ilrma.run(X, iteration=2, n_basis=2, W=W0, T=T0, V=V0)
     want = [7.2776542359e5, 4.3845892818e4, 2.8737622949e4]
     assert np.allclose(loss, want, rtol=1e-9)
+
+
+def test_consistent_ilrma_is_projection_back_ilrma():
+    """ConsistentGaussILRMA (src/bss/ilrma.py:1102-1233): the STFT-consistency projection never reaches the IP update, so
+    the reference's result equals Gauss-ILRMA with projection-back normalisation (fixture generated from the reference)."""
+    meta, i, o = load_golden('ilrma_consistent')
+    out, st, loss = ilrma.run(i['X'], iteration=meta['iteration'], n_basis=meta['n_basis'], spatial='IP', domain=2,
+                              normalize_mode='projection-back', W=i['W0'], T=i['T0'], V=i['V0'])
+    assert rel(out, o['output']) < TOL and rel(loss, o['loss']) < TOL and rel(st['W'], o['demix_filter']) < TOL
+
+
+def test_stft_fixture_matches_scipy():
+    """The reference's stft/istft are thin wrappers of scipy.signal (src/transform/stft.py:4-17): the fixture written from
+    the reference must equal a direct scipy call, which is what the GPU tests use as the run-time oracle."""
+    from scipy import signal as ss
+    meta, i, o = load_golden('ilrma_consistent')
+    n, h = meta['fft_size'], meta['hop_size']
+    Z = ss.stft(i['x'], nperseg=n, noverlap=n - h, window='hann')[2]
+    assert rel(Z, o['stft']) < 1e-14
+    y = ss.istft(Z, nperseg=n, noverlap=n - h, window='hann')[1][..., :meta['n_samples']]
+    assert rel(y, o['istft']) < 1e-12
