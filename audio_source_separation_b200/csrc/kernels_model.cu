@@ -214,39 +214,57 @@ __global__ void __launch_bounds__(256) export_y_kernel(const cf* Y, const double
 // ------------------------------------------------------------------------------------------- loss
 // per bin: sum_{n,t} (P/R + log R)            (mode 0, src/bss/ilrma.py:669-676)
 //          sum_{n,t} ((1+nu/2) log(1 + (2/nu) P/R) + log R)   (mode 1, src/bss/ilrma.py:1012-1019)
+// Same streaming structure as the covariance kernel: CTA-contiguous bin ranges, activation rows cached in shared
+// memory (CACHE), n_basis = 2 resolved at compile time (KT).
 struct LossParams {
     MuArgs a;
     double* out;   // [B][F]
     float expo;    // 2/domain
     TileGeom g;
     long long n_items;
-    uint32_t scratch_off, scratch_stride, ring_off;
+    uint32_t scratch_off, scratch_stride, ring_off, cache_off;
 };
 
-template <int C, bool FROM_Y>
-__global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
+template <int C, int KT, bool FROM_Y, bool CACHE>
+__global__ void __launch_bounds__(512, 1) ilrma_loss_kernel(const LossParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     const MuArgs& a = p.a;
     constexpr int N = C;
-    const int K = a.K;
+    const int K = KT > 0 ? KT : a.K;
+    const int Tp = a.Tp;
     float* tb = reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride);
+    int lo, hi;
+    cta_item_range((int)p.n_items, lo, hi);
     WarpStream<MU_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
-             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X,
-             (int)(blockIdx.x * wpc + warp), (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
+             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X, lo + warp, wpc, hi, 1, lane);
+    const float* vcache = reinterpret_cast<const float*>(smem + p.cache_off);
+    int b_lo = 0;
+    if (CACHE) b_lo = load_act_cache(reinterpret_cast<float*>(smem + p.cache_off), a.act, N * K * Tp, lo, hi, 1, a.F);
     cf w[C][C];
+    float tkr[N][KT > 0 ? KT : 1];
     double total = 0.0;
+    int b = 0, voff = 0;
 #pragma unroll 1
     while (st.active()) {
         st.issue_next(p.g, (FROM_Y ? a.Y : a.X), 1);
         const int bf = st.cons.item;
-        const int b = (int)(bf / a.F), f = bf - b * a.F;
         if (st.first_slab()) {
-            for (int i = lane; i < N * K; i += 32) {
-                const int n = i / K, k = i - n * K;
-                tb[i] = a.basis[(((size_t)b * N + n) * a.F + f) * K + k];
+            b = bf / a.F;
+            const int f = bf - b * a.F;
+            voff = (b - b_lo) * N * K * Tp;
+            if (KT > 0) {
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+#pragma unroll
+                    for (int k = 0; k < (KT > 0 ? KT : 1); ++k) tkr[n][k] = __ldg(a.basis + (((size_t)b * N + n) * a.F + f) * K + k);
+            } else {
+                for (int i = lane; i < N * K; i += 32) {
+                    const int n = i / K, k = i - n * K;
+                    tb[i] = a.basis[(((size_t)b * N + n) * a.F + f) * K + k];
+                }
             }
             load_filter<C, FROM_Y>(w, a.Wf + (size_t)bf * C * C);
             total = 0.0;
@@ -266,13 +284,22 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
             const int t = tbase + tt;
 #pragma unroll
             for (int n = 0; n < N; ++n) {
-                const float* v = a.act + ((size_t)b * N + n) * K * a.Tp + t;
+                const float* v = CACHE ? vcache + voff + n * K * Tp + t : a.act + ((size_t)b * N + n) * K * Tp + t;
                 float r0 = 0.f, r1 = 0.f;
-                for (int k = 0; k < K; ++k) {
-                    const float2 vv = __ldg(reinterpret_cast<const float2*>(v + (size_t)k * a.Tp));
-                    const float tk = tb[n * K + k];
-                    r0 = fmaf(tk, vv.x, r0);
-                    r1 = fmaf(tk, vv.y, r1);
+                if (KT > 0) {
+#pragma unroll
+                    for (int k = 0; k < (KT > 0 ? KT : 1); ++k) {
+                        const float2 vv = CACHE ? *reinterpret_cast<const float2*>(v + k * Tp) : __ldg(reinterpret_cast<const float2*>(v + (size_t)k * Tp));
+                        r0 = fmaf(tkr[n][k], vv.x, r0);
+                        r1 = fmaf(tkr[n][k], vv.y, r1);
+                    }
+                } else {
+                    for (int k = 0; k < K; ++k) {
+                        const float2 vv = CACHE ? *reinterpret_cast<const float2*>(v + k * Tp) : __ldg(reinterpret_cast<const float2*>(v + (size_t)k * Tp));
+                        const float tk = tb[n * K + k];
+                        r0 = fmaf(tk, vv.x, r0);
+                        r1 = fmaf(tk, vv.y, r1);
+                    }
                 }
                 if (p.expo != 1.f) {
                     r0 = powf(r0, p.expo);
@@ -282,8 +309,8 @@ __global__ void __launch_bounds__(256) ilrma_loss_kernel(const LossParams p) {
                 r1 = r1 < a.eps ? a.eps : r1;
                 float l0, l1;
                 if (a.mode == 0) {
-                    l0 = P0[n] / r0 + logf(r0);
-                    l1 = P1[n] / r1 + logf(r1);
+                    l0 = P0[n] * rcp_fast(r0) + __logf(r0);
+                    l1 = P1[n] * rcp_fast(r1) + __logf(r1);
                 } else {
                     l0 = (1.f + 0.5f * a.nu) * log1pf((2.f / a.nu) * (P0[n] / r0)) + logf(r0);
                     l1 = (1.f + 0.5f * a.nu) * log1pf((2.f / a.nu) * (P1[n] / r1)) + logf(r1);
@@ -428,7 +455,21 @@ int launch_export_y(bss_handle* h, const cf* Y, const double2* scale, cf* out, i
     return BSS_OK;
 }
 
-template <int C, bool FROM_Y>
+template <int C, int KT, bool FROM_Y, bool CACHE>
+static int launch_ilrma_loss_c(bss_handle* h, const LossParams& p, const StreamPlan& sp, size_t smem_bytes) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        BSS_CUDA(h, cudaFuncSetAttribute(ilrma_loss_kernel<C, KT, FROM_Y, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->max_smem));
+        attr_done = true;
+    }
+    ilrma_loss_kernel<C, KT, FROM_Y, CACHE><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+template <int C, int KT, bool FROM_Y>
 static int launch_ilrma_loss_t(bss_handle* h, const MuArgs& a, float expo, double* terms) {
     LossParams p;
     p.a = a;
@@ -436,28 +477,30 @@ static int launch_ilrma_loss_t(bss_handle* h, const MuArgs& a, float expo, doubl
     p.expo = expo;
     p.g = make_tile_geom(C, a.Tp);
     p.n_items = (long long)a.B * a.F;
+    p.cache_off = 0;
+    const size_t scratch = KT > 0 ? 16 : (size_t)C * a.K * 4;
     StreamPlan sp;
-    if (!plan_stream(h, p.g, MU_STAGES, (size_t)C * a.K * 4, (int)p.n_items, 8, &sp))
+    size_t smem_bytes = 0;
+    const bool cached = plan_stream_cached(h, p.g, MU_STAGES, scratch, p.n_items, 16, (size_t)C * a.K * a.Tp * sizeof(float), a.F, &sp,
+                                           &p.cache_off, &smem_bytes);
+    if (!cached && !plan_stream(h, p.g, MU_STAGES, scratch, p.n_items, 16, &sp))
         return bss_fail(h, BSS_EINVAL, "loss: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
     p.ring_off = sp.ring_off;
-    static bool attr_done = false;
-    if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(ilrma_loss_kernel<C, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         h->max_smem));
-        attr_done = true;
-    }
-    ilrma_loss_kernel<C, FROM_Y><<<sp.grid, sp.wpc * 32, sp.smem_bytes, h->stream>>>(p);
-    h->launches++;
-    BSS_CUDA(h, cudaGetLastError());
-    return BSS_OK;
+    if (cached) return launch_ilrma_loss_c<C, KT, FROM_Y, true>(h, p, sp, smem_bytes);
+    return launch_ilrma_loss_c<C, KT, FROM_Y, false>(h, p, sp, sp.smem_bytes);
 }
 
 int launch_ilrma_loss(bss_handle* h, const MuArgs& a, float expo, double* terms) {
     int rc = BSS_OK;
-    if (a.Y) { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, true>(h, a, expo, terms))) }
-    else { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, false>(h, a, expo, terms))) }
+    if (a.K == 2) {
+        if (a.Y) { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, 2, true>(h, a, expo, terms))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, 2, false>(h, a, expo, terms))) }
+    } else {
+        if (a.Y) { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, 0, true>(h, a, expo, terms))) }
+        else { BSS_DISPATCH_C(a.C, (rc = launch_ilrma_loss_t<CC_, 0, false>(h, a, expo, terms))) }
+    }
     return rc;
 }
 
