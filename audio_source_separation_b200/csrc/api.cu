@@ -1,6 +1,7 @@
 // C ABI of libbssgpu.so (see include/bssgpu.h): handle life cycle, host <-> device state
 // movement and the orchestration of one update_once per method.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -167,6 +168,7 @@ void bss_destroy(bss_handle* h) {
     for (void* p : bufs)
         if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -278,11 +280,10 @@ int bss_update_once(bss_handle* h) {
     return bss_fail(h, BSS_EINVAL, "unknown method");
 }
 
-int bss_run(bss_handle* h, int n_iter) {
-    if (!h || n_iter < 0) return BSS_EINVAL;
+// n eager iterations (advances the IP2 pair schedule like the reference's __call__, src/bss/ilrma.py:635-646)
+static int run_eager(bss_handle* h, int n_iter) {
     for (int i = 0; i < n_iter; ++i) {
         if (!is_nmf(h->cfg.method) && h->cfg.spatial == BSS_SPATIAL_IP2 && h->cfg.method != BSS_FAST_MNMF) {
-            // src/bss/ilrma.py:635-646: (0,1) first, then +1 modulo N
             if (h->pair_m < 0) {
                 h->pair_m = 0;
                 h->pair_n = 1;
@@ -294,6 +295,52 @@ int bss_run(bss_handle* h, int n_iter) {
         BSS_TRY(bss_update_once(h));
     }
     return BSS_OK;
+}
+
+// Long loops are replayed from a CUDA graph: small problems (one mixture, NMF) are bound by launch latency, and a graph
+// of two iterations (two, because the basis / spatial buffers are double buffered and swap every iteration) removes the
+// host from the loop.  IP2 changes its kernel arguments every iteration (the update pair) and stays eager.
+static bool graph_capable(const bss_handle* h) {
+    if (getenv("BSSGPU_NO_GRAPH")) return false;
+    if (!is_nmf(h->cfg.method) && h->cfg.method != BSS_FAST_MNMF && h->cfg.spatial == BSS_SPATIAL_IP2) return false;
+    return true;
+}
+
+int bss_run(bss_handle* h, int n_iter) {
+    if (!h || n_iter < 0) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int kPerGraph = 2, kWarm = 2, kMinReplays = 4;
+    if (n_iter < kWarm + kPerGraph * kMinReplays || !graph_capable(h)) return run_eager(h, n_iter);
+    // eager warm-up: every scratch buffer reaches its final size and every kernel attribute is set before the capture
+    BSS_TRY(run_eager(h, kWarm));
+    n_iter -= kWarm;
+    if (h->graph_exec) {
+        cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return run_eager(h, n_iter);
+    }
+    const int rc_cap = run_eager(h, kPerGraph);
+    const cudaError_t e_end = cudaStreamEndCapture(h->stream, &graph);
+    const int64_t per_graph = h->launches - l0;
+    h->launches = l0;   // nothing of the capture has executed
+    cudaGraphExec_t exec = nullptr;
+    if (rc_cap != BSS_OK || e_end != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        if (rc_cap != BSS_OK) return rc_cap;
+        return run_eager(h, n_iter);
+    }
+    cudaGraphDestroy(graph);
+    h->graph_exec = exec;
+    const int reps = n_iter / kPerGraph;
+    for (int r = 0; r < reps; ++r) BSS_CUDA(h, cudaGraphLaunch(exec, h->stream));
+    h->launches += per_graph * reps;
+    return run_eager(h, n_iter - reps * kPerGraph);
 }
 
 // one loss evaluation queued on the stream; result at lossbuf[B*F .. B*F+B)

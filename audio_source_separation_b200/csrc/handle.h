@@ -26,6 +26,7 @@ struct bss_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    void* graph_exec = nullptr;    // cudaGraphExec_t of the last captured pair of iterations (bss_run)
     std::string err;
 
     bool has_input = false;

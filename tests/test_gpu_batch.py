@@ -57,3 +57,70 @@ def test_batch_handles_are_independent(cuda_device):
     for i in (0, 1, 3):
         assert np.array_equal(a[i], b[i])
     assert not np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize('kind', ['ilrma_ip', 'ilrma_iss', 'ilrma_part', 'auxiva', 'fastmnmf', 'nmf'])
+def test_graph_replay_equals_eager_loop(cuda_device, kind, monkeypatch):
+    """bss_run replays long loops from a CUDA graph of two iterations; the result must be bit-identical to the eager
+    loop (same kernels, same order), including an odd number of iterations."""
+    import warnings
+    from audio_source_separation_b200 import _lib
+    rng = np.random.default_rng(0)
+    n_iter = 25
+
+    def build():
+        C, F, T, K = 3, 40, 150, 2
+        X = synth.mix2(C, F, T, seed=4)
+        common = dict(n_batch=1, n_channels=C, n_sources=C, n_bins=F, n_frames=T, n_basis=K)
+        if kind == 'nmf':
+            h = _lib.Handle(method=_lib.NMF_EUC, n_batch=1, n_channels=1, n_sources=1, n_bins=F, n_frames=T, n_basis=K)
+            h.set_state(_lib.STATE_TARGET, np.abs(X[0]) ** 2, np.float64)
+            h.set_state(_lib.STATE_BASIS, np.random.default_rng(1).random((F, K)), np.float64)
+            h.set_state(_lib.STATE_ACTIVATION, np.random.default_rng(2).random((K, T)), np.float64)
+            return h, [(_lib.STATE_BASIS, (F, K), np.float64), (_lib.STATE_ACTIVATION, (K, T), np.float64)]
+        if kind == 'fastmnmf':
+            h = _lib.Handle(method=_lib.FAST_MNMF, **common)
+            h.set_input(X)
+            h.reset_spatial()
+            h.set_state(_lib.STATE_BASIS, np.random.default_rng(1).random((C, F, K)), np.float64)
+            h.set_state(_lib.STATE_ACTIVATION, np.random.default_rng(2).random((C, K, T)), np.float64)
+            return h, [(_lib.STATE_DIAGONALIZER, (F, C, C), np.complex128), (_lib.STATE_SPATIAL, (C, F, C), np.float64),
+                       (_lib.STATE_BASIS, (C, F, K), np.float64)]
+        if kind == 'auxiva':
+            h = _lib.Handle(method=_lib.AUX_LAPLACE_IVA, normalize=_lib.NORMALIZE_NONE, **common)
+            h.set_input(X)
+            h.reset_spatial()
+            return h, [(_lib.STATE_DEMIX_FILTER, (F, C, C), np.complex128)]
+        part = kind == 'ilrma_part'
+        h = _lib.Handle(method=_lib.GAUSS_ILRMA, spatial=_lib.SPATIAL_ISS if kind == 'ilrma_iss' else _lib.SPATIAL_IP,
+                        partitioning=1 if part else 0, **common)
+        h.set_input(X)
+        h.reset_spatial()
+        if part:
+            Z = np.random.default_rng(3).random((C, K)) + 0.5
+            h.set_state(_lib.STATE_LATENT, Z / Z.sum(axis=0), np.float64)
+            h.set_state(_lib.STATE_BASIS, np.random.default_rng(1).random((F, K)), np.float64)
+            h.set_state(_lib.STATE_ACTIVATION, np.random.default_rng(2).random((K, T)), np.float64)
+            return h, [(_lib.STATE_DEMIX_FILTER, (F, C, C), np.complex128), (_lib.STATE_BASIS, (F, K), np.float64),
+                       (_lib.STATE_LATENT, (C, K), np.float64)]
+        h.set_state(_lib.STATE_BASIS, np.random.default_rng(1).random((C, F, K)), np.float64)
+        h.set_state(_lib.STATE_ACTIVATION, np.random.default_rng(2).random((C, K, T)), np.float64)
+        return h, [(_lib.STATE_ESTIMATION, (C, F, T), np.complex128), (_lib.STATE_BASIS, (C, F, K), np.float64),
+                   (_lib.STATE_ACTIVATION, (C, K, T), np.float64)]
+
+    results = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv('BSSGPU_NO_GRAPH', '1')
+        else:
+            monkeypatch.delenv('BSSGPU_NO_GRAPH', raising=False)
+        h, states = build()
+        n0 = h.launch_count()
+        h.run(n_iter)
+        h.synchronize()
+        results.append(([h.get_state(w, shape, dt) for w, shape, dt in states], h.launch_count() - n0))
+        h.close()
+    (graph_states, graph_launches), (eager_states, eager_launches) = results
+    assert graph_launches == eager_launches          # replayed launches are counted
+    for a, b in zip(graph_states, eager_states):
+        assert np.array_equal(a, b)
