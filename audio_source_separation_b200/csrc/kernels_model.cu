@@ -45,46 +45,44 @@ __device__ __forceinline__ void frame_power(const float4 (&xv)[C], const cf (&w)
 
 // ------------------------------------------------------------------------------------------- normalisation
 // aux_n = max(sqrt(mean_f pw[n,f]), eps);  W[:,n,:] /= aux_n;  T[n] /= aux_n^domain     src/bss/ilrma.py:305-322
-// grid (blocks_per_mixture, B); every block recomputes the N scalars (deterministic, fp64).
-__global__ void __launch_bounds__(256) normalize_power_kernel(double2* W, cf* Wf, float* basis, const double* pw, int N, int C,
-                                                              int F, int K, double domain, double eps, double* aux_out) {
-    __shared__ double red[8][8];
-    __shared__ double aux_s[8];
-    const int b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int n = 0; n < N; ++n) {
-        double s = 0.0;
-        for (int f = threadIdx.x; f < F; f += blockDim.x) s += pw[((size_t)b * N + n) * F + f];
-        s = warp_sum(s);
-        if (lane == 0) red[n][warp] = s;
-    }
+// Two launches: one block per (mixture, source) reduces the per-bin powers in a fixed order (fp64, deterministic),
+// then a fully parallel pass rescales the filters, their fp32 mirror and the basis.
+__global__ void __launch_bounds__(256) power_aux_kernel(const double* pw, double* aux, int F, double eps) {
+    __shared__ double red[8];
+    const long long bn = blockIdx.x;
+    double s = 0.0;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) s += pw[(size_t)bn * F + f];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x < N) {
-        double s = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-        double aux = sqrt(s / (double)F);
-        if (aux < eps) aux = eps;
-        aux_s[threadIdx.x] = aux;
-        if (blockIdx.x == 0 && aux_out) aux_out[(size_t)b * N + threadIdx.x] = aux;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        const double a = sqrt(t / (double)F);
+        aux[bn] = a < eps ? eps : a;
     }
-    __syncthreads();
-    const long long nW = (long long)F * N * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nW; i += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)((i / C) % N);
-        const double inv = 1.0 / aux_s[n];
-        double2 v = W[(size_t)b * nW + i];
+}
+
+__global__ void __launch_bounds__(256) normalize_power_kernel(double2* W, cf* Wf, float* basis, const double* aux, int B, int N, int C,
+                                                              int F, int K, double domain) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nW = (long long)B * F * N * C;
+    const long long nT = basis ? (long long)B * N * F * K : 0;
+    if (idx < nW) {
+        const int n = (int)((idx / C) % N);
+        const int b = (int)(idx / ((long long)F * N * C));
+        const double inv = 1.0 / aux[(size_t)b * N + n];
+        double2 v = W[idx];
         v.x *= inv;
         v.y *= inv;
-        W[(size_t)b * nW + i] = v;
-        Wf[(size_t)b * nW + i] = cf_make((float)v.x, (float)v.y);
-    }
-    if (basis) {
-        const long long nT = (long long)N * F * K;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nT; i += (long long)gridDim.x * blockDim.x) {
-            const int n = (int)(i / ((long long)F * K));
-            const double sc = domain == 2.0 ? aux_s[n] * aux_s[n] : pow(aux_s[n], domain);
-            basis[(size_t)b * nT + i] = (float)((double)basis[(size_t)b * nT + i] / sc);
-        }
+        W[idx] = v;
+        Wf[idx] = cf_make((float)v.x, (float)v.y);
+    } else if (idx < nW + nT) {
+        const long long i = idx - nW;
+        const long long bn = i / ((long long)F * K);
+        const double a = aux[bn];
+        const double sc = domain == 2.0 ? a * a : pow(a, domain);
+        basis[i] = (float)((double)basis[i] / sc);
     }
 }
 
@@ -385,8 +383,11 @@ __global__ void __launch_bounds__(256) import_x_kernel(const TIn* in, cf* X, int
 
 int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, const double* pw, int B, int N, int C, int F, int K,
                            double domain, double eps, double* aux_out) {
-    dim3 grid(8, B);
-    normalize_power_kernel<<<grid, 256, 0, h->stream>>>(W, Wf, basis, pw, N, C, F, K, domain, eps, aux_out);
+    power_aux_kernel<<<B * N, 256, 0, h->stream>>>(pw, aux_out, F, eps);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    const long long n = (long long)B * F * N * C + (basis ? (long long)B * N * F * K : 0);
+    normalize_power_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(W, Wf, basis, aux_out, B, N, C, F, K, domain);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;

@@ -386,27 +386,41 @@ __global__ void __launch_bounds__(128) mu_act_partial_kernel(const MuArgs a, flo
 }
 
 // Stage 2: fixed-order sum over the chunks (deterministic), then V <- V (num/den)^q, in place.
+// Block = 32 frames x 8 chunk lanes: lane y sums chunks y, y+8, ..., then the 8 partial sums are added in order.
 __global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, const float* part, float* act, int N, int n_chunks) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)a.B * N * a.K * a.Tp;
-    if (idx >= total) return;
-    const int t = (int)(idx % a.Tp);
-    long long r = idx / a.Tp;
-    const int k = (int)(r % a.K);
-    r /= a.K;
-    const int n = (int)(r % N);
-    const int b = (int)(r / N);
+    __shared__ float red[2][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int t_tiles = (a.Tp + 31) / 32;
+    const long long row = blockIdx.x / t_tiles;          // (b, n, k)
+    const int t = (int)(blockIdx.x % t_tiles) * 32 + tx;
+    const int k = (int)(row % a.K);
+    const long long bn = row / a.K;
+    const int n = (int)(bn % N);
+    const int b = (int)(bn / N);
+    float num = 0.f, den = 0.f;
+    if (t < a.Tp) {
+        for (int c = ty; c < n_chunks; c += 8) {
+            const float* src = part + (((((size_t)b * n_chunks + c) * N + n) * a.K + k) * 2) * a.Tp + t;
+            num += src[0];
+            den += src[a.Tp];
+        }
+    }
+    red[0][ty][tx] = num;
+    red[1][ty][tx] = den;
+    __syncthreads();
+    if (ty != 0 || t >= a.Tp) return;
+    const size_t idx = (size_t)row * a.Tp + t;
     if (t >= a.T) {
         act[idx] = 0.f;
         return;
     }
     const bool sel = a.sel_m < 0 || n == a.sel_m || n == a.sel_n;
     if (!sel) return;
-    float num = 0.f, den = 0.f;
-    for (int c = 0; c < n_chunks; ++c) {
-        const float* src = part + (((((size_t)b * n_chunks + c) * N + n) * a.K + k) * 2) * a.Tp + t;
-        num += src[0];
-        den += src[a.Tp];
+    num = den = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        num += red[0][y][tx];
+        den += red[1][y][tx];
     }
     den = fmaxf(den, a.eps);
     act[idx] = act[idx] * pow_q(num / den, a.q_exp);
@@ -679,8 +693,8 @@ int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_ou
         if (done) {
             if (n_chunks_out) *n_chunks_out = n_chunks_s;
             if (!act) return BSS_OK;
-            const long long total = (long long)a.B * C * a.K * a.Tp;
-            mu_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, act, C, n_chunks_s);
+            const long long blocks = (long long)a.B * C * a.K * ((a.Tp + 31) / 32);
+            mu_act_finish_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(a, h->part, act, C, n_chunks_s);
             h->launches++;
             BSS_CUDA(h, cudaGetLastError());
             return BSS_OK;
@@ -720,8 +734,8 @@ int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_ou
     BSS_CUDA(h, cudaGetLastError());
     if (n_chunks_out) *n_chunks_out = n_chunks;
     if (!act) return BSS_OK;
-    const long long total = (long long)a.B * C * a.K * a.Tp;
-    mu_act_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(a, h->part, act, C, n_chunks);
+    const long long blocks = (long long)a.B * C * a.K * ((a.Tp + 31) / 32);
+    mu_act_finish_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(a, h->part, act, C, n_chunks);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;

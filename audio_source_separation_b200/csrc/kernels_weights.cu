@@ -69,22 +69,31 @@ __global__ void __launch_bounds__(128) frame_power_partial_kernel(const cf* src,
 }
 
 // Stage 2: r = sqrt(sum) (Laplace) or sum / F (Gauss); inverse of the floored value for the covariance
-// kernel, raw value for the loss.  kind: 0 Laplace, 1 Gauss.
+// kernel, raw value for the loss.  kind: 0 Laplace, 1 Gauss.  Block = 32 frames x 8 chunk lanes, fixed summation order.
 __global__ void __launch_bounds__(256) frame_weight_finish_kernel(const float* part, float* winv, float* raw, int B, int N, int F,
                                                                  int T, int Tp, int n_chunks, int kind, float eps) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)B * N * Tp) return;
-    const int t = (int)(idx % Tp);
-    const long long bn = idx / Tp;
+    __shared__ float red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int t_tiles = (Tp + 31) / 32;
+    const long long bn = blockIdx.x / t_tiles;
+    const int t = (int)(blockIdx.x % t_tiles) * 32 + tx;
     const int n = (int)(bn % N);
     const int b = (int)(bn / N);
+    float s = 0.f;
+    if (t < Tp)
+        for (int c = ty; c < n_chunks; c += 8) s += part[(((size_t)b * n_chunks + c) * N + n) * Tp + t];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty != 0 || t >= Tp) return;
+    const size_t idx = (size_t)bn * Tp + t;
     if (t >= T) {
         if (winv) winv[idx] = 1.f;
         if (raw) raw[idx] = 0.f;
         return;
     }
-    float s = 0.f;
-    for (int c = 0; c < n_chunks; ++c) s += part[(((size_t)b * n_chunks + c) * N + n) * Tp + t];
+    s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][tx];
     const float r = kind == 0 ? sqrtf(s) : s / (float)F;
     if (raw) raw[idx] = r;
     if (winv) winv[idx] = __frcp_rn(r < eps ? eps : r);
@@ -213,9 +222,8 @@ int launch_frame_weights(bss_handle* h, const cf* src, const cf* Wf, int from_y,
     }
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
-    const long long total = (long long)B * C * Tp;
-    frame_weight_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, h->stream>>>(h->part, winv, raw, B, C, F, T, Tp, n_chunks,
-                                                                                  kind, eps);
+    const long long blocks = (long long)B * C * ((Tp + 31) / 32);
+    frame_weight_finish_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->part, winv, raw, B, C, F, T, Tp, n_chunks, kind, eps);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
