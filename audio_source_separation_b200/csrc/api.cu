@@ -403,19 +403,20 @@ int bss_separate(bss_handle* h, void* y, int dtype, int apply_projection_back) {
     if (dtype != BSS_C64 && dtype != BSS_C128) return bss_fail(h, BSS_EINVAL, "output must be complex64 or complex128");
     const size_t elems = (size_t)h->B * h->N * h->F * h->T;
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
-    BSS_TRY(ensure_staging(h, elems * 8));
-    BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
     if (dtype == BSS_C64) {
+        BSS_TRY(ensure_staging(h, elems * 8));
+        BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
         BSS_CUDA(h, cudaMemcpyAsync(y, h->staging, elems * 8, cudaMemcpyDeviceToHost, h->stream));
         return check_flags(h);
     }
-    BSS_TRY(ensure_pinned(h, elems * 8));
-    BSS_CUDA(h, cudaMemcpyAsync(h->pinned, h->staging, elems * 8, cudaMemcpyDeviceToHost, h->stream));
-    BSS_TRY(check_flags(h));
-    const float* s = (const float*)h->pinned;
-    double* d = (double*)y;
-    for (size_t i = 0; i < elems * 2; ++i) d[i] = (double)s[i];
-    return BSS_OK;
+    // complex128 for the caller: widen on the device and copy straight into the caller's array (no pinned bounce buffer,
+    // no host-side conversion loop)
+    BSS_TRY(ensure_staging(h, elems * 24));
+    cf* narrow = (cf*)((char*)h->staging + elems * 16);
+    BSS_TRY(bss_separate_device(h, narrow, apply_projection_back));
+    BSS_TRY(launch_widen(h, narrow, (double2*)h->staging, (long long)elems));
+    BSS_CUDA(h, cudaMemcpyAsync(y, h->staging, elems * 16, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h);
 }
 
 int bss_compute_demix_filter(bss_handle* h) {

@@ -242,6 +242,7 @@ int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, cons
 int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const double2* scale, int B, int N, int C, int F, int K,
                         double domain);
 int launch_sync_wf(bss_handle* h, const double2* W, cf* Wf, long long n);
+int launch_widen(bss_handle* h, const cf* in, double2* out, long long n);
 int launch_separate(bss_handle* h, const cf* X, const cf* Wf, const double2* scale, cf* Y, cf* out, int B, int C, int F, int T,
                     int Tp);
 int launch_export_y(bss_handle* h, const cf* Y, const double2* scale, cf* out, int B, int N, int F, int T, int Tp);

@@ -112,6 +112,11 @@ __global__ void __launch_bounds__(256) normalize_pb_kernel(double2* W, cf* Wf, f
     }
 }
 
+__global__ void __launch_bounds__(256) widen_kernel(const cf* in, double2* out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2((double)in[i].x, (double)in[i].y);
+}
+
 __global__ void __launch_bounds__(256) sync_wf_kernel(const double2* W, cf* Wf, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) Wf[i] = cf_make((float)W[i].x, (float)W[i].y);
@@ -397,6 +402,13 @@ int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const d
                         double domain) {
     const long long n = (long long)B * F * N;
     normalize_pb_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(W, Wf, basis, scale, B, N, C, F, K, domain);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_widen(bss_handle* h, const cf* in, double2* out, long long n) {
+    widen_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(in, out, n);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
