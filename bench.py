@@ -205,6 +205,9 @@ def run_gpu_arm(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
