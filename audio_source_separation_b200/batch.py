@@ -159,6 +159,11 @@ def gather_outputs(local, world_size, group=None):
     import torch.distributed as dist
     if world_size == 1:
         return local
-    parts = [torch.empty_like(local) for _ in range(world_size)]
-    dist.all_gather(parts, local, group=group)
-    return torch.cat(parts, dim=0)
+    out = torch.empty((world_size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    try:
+        # one collective straight into the final buffer (rank order == batch order)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):
+        parts = list(out.chunk(world_size, dim=0))
+        dist.all_gather(parts, local.contiguous(), group=group)
+    return out
