@@ -65,6 +65,7 @@ SIGNATURES = {
     'bss_loss': (_i, [_vp, ctypes.POINTER(_d)]),
     'bss_separate': (_i, [_vp, _vp, _i, _i]),
     'bss_separate_device': (_i, [_vp, _vp, _i]),
+    'bss_separate_waveform': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     'bss_compute_demix_filter': (_i, [_vp]),
     'bss_weighted_covariance': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'bss_ip_update': (_i, [_i, _i, _i, _vp, _vp, _vp, _d, _i, _d]),
@@ -231,6 +232,15 @@ class Handle:
 
     def separate_into(self, ptr, dtype, projection_back=True):
         self._check(self._lib.bss_separate(self._h, ctypes.c_void_p(ptr), dtype, 1 if projection_back else 0))
+
+    def separate_waveform(self, n_signals_shape, fft_size, hop_size, window, dtype=np.float64, projection_back=True):
+        """Separated estimates in the time domain, shape `n_signals_shape + (n_out,)` (ISTFT on the device)."""
+        window = as_host(window, np.float64)
+        n_out = self._lib.bss_istft_length(self.cfg['n_frames'], int(fft_size), int(hop_size))
+        out = np.empty(tuple(n_signals_shape) + (n_out,), dtype=dtype)
+        self._check(self._lib.bss_separate_waveform(self._h, _ptr(out), _DTYPES[out.dtype], int(fft_size), int(hop_size), _ptr(window),
+                                                    1 if projection_back else 0))
+        return out
 
     def separate_device(self, device_ptr, projection_back=True):
         self._check(self._lib.bss_separate_device(self._h, ctypes.c_void_p(device_ptr), 1 if projection_back else 0))

@@ -419,6 +419,17 @@ int bss_separate(bss_handle* h, void* y, int dtype, int apply_projection_back) {
     return check_flags(h);
 }
 
+int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int hop_size, const double* window,
+                          int apply_projection_back) {
+    if (!h || !y || !window) return BSS_EINVAL;
+    const size_t elems = (size_t)h->B * h->N * h->F * h->T;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    BSS_TRY(ensure_staging(h, elems * 8));
+    BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
+    BSS_TRY(istft_from_device(h, (const cf*)h->staging, h->B * h->N, fft_size, hop_size, window, y, dtype));
+    return check_flags(h);
+}
+
 int bss_compute_demix_filter(bss_handle* h) {
     if (!h) return BSS_EINVAL;
     if (is_nmf(h->cfg.method) || h->cfg.method == BSS_FAST_MNMF) return bss_fail(h, BSS_EINVAL, "no demixing filter");

@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(1024) stft_kernel(const StftParams p) {
     }
 }
 
+template <typename TZ>
 struct IstftParams {
-    const double2* z;    // [S][N/2+1][n_frames]
+    const TZ* z;         // [S][N/2+1][n_frames]  (double2 or float2)
     const float* win;
     const float2* tw;
     int S, N, hop, n_frames;
@@ -89,16 +90,17 @@ struct IstftParams {
     float* frames;       // [S][n_frames][N]
 };
 
-__global__ void __launch_bounds__(1024) istft_frames_kernel(const IstftParams p) {
+template <typename TZ>
+__global__ void __launch_bounds__(1024) istft_frames_kernel(const IstftParams<TZ> p) {
     extern __shared__ __align__(16) float2 fft_smem[];
     const int N = p.N, M = N >> 1;
     float2* a = fft_smem;
     float2* b = fft_smem + M;
     const int frame = blockIdx.x, s = blockIdx.y;
-    const double2* z = p.z + (size_t)s * (M + 1) * p.n_frames + frame;
+    const TZ* z = p.z + (size_t)s * (M + 1) * p.n_frames + frame;
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
-        const double2 xk = z[(size_t)k * p.n_frames];
-        const double2 xm = z[(size_t)(M - k) * p.n_frames];
+        const TZ xk = z[(size_t)k * p.n_frames];
+        const TZ xm = z[(size_t)(M - k) * p.n_frames];
         const float2 w = __ldg(p.tw + k);
         // Z[k] = (Xk + conj(Xm)) / 2 + (i / 2) conj(w) (Xk - conj(Xm));  stored conjugated for the inverse transform
         const float2 e = make_float2(0.5f * (float)(xk.x + xm.x), 0.5f * (float)(xk.y - xm.y));
@@ -117,7 +119,8 @@ __global__ void __launch_bounds__(1024) istft_frames_kernel(const IstftParams p)
 }
 
 // overlap-add, squared-window normalisation, boundary trim
-__global__ void __launch_bounds__(256) istft_ola_kernel(const float* frames, const float* win, double* out, int S, int N, int hop,
+template <typename TO>
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* frames, const float* win, TO* out, int S, int N, int hop,
                                                         int n_frames, int out_len) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)S * out_len) return;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* frames, con
         acc += frames[((size_t)s * n_frames + ii) * N + r];
         norm += win[r] * win[r];
     }
-    out[idx] = (double)(norm > 1e-10f ? acc / norm : acc);
+    out[idx] = (TO)(norm > 1e-10f ? acc / norm : acc);
 }
 
 __global__ void __launch_bounds__(256) to_float_kernel(const double* in, float* out, long long n) {
@@ -285,7 +288,7 @@ int bss_istft(int device, int n_signals, int n_frames, int fft_size, int hop_siz
         rc = BSS_ENOMEM;
     if (rc == BSS_OK) {
         cudaMemcpy(zd, z, n_in * sizeof(double2), cudaMemcpyHostToDevice);
-        IstftParams p{};
+        IstftParams<double2> p{};
         p.z = zd;
         p.win = t.win;
         p.tw = t.tw;
@@ -296,11 +299,11 @@ int bss_istft(int device, int n_signals, int n_frames, int fft_size, int hop_siz
         p.scale = (float)(t.win_sum / (double)(fft_size / 2));
         p.frames = frames;
         const size_t smem = (size_t)fft_size * sizeof(float2);
-        cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(istft_frames_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(n_frames, n_signals);
-        istft_frames_kernel<<<grid, fft_threads(fft_size), smem>>>(p);
+        istft_frames_kernel<double2><<<grid, fft_threads(fft_size), smem>>>(p);
         const long long n = (long long)n_signals * out_len;
-        istft_ola_kernel<<<(unsigned)cdiv(n, 256), 256>>>(frames, t.win, od, n_signals, fft_size, hop_size, n_frames, out_len);
+        istft_ola_kernel<double><<<(unsigned)cdiv(n, 256), 256>>>(frames, t.win, od, n_signals, fft_size, hop_size, n_frames, out_len);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpy(out, od, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = BSS_ECUDA;
@@ -327,5 +330,57 @@ int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int
                                h->Tp, n_frames);
     if (rc != BSS_OK) return bss_fail(h, rc, "stft failed");
     h->launches += 1;
+    return BSS_OK;
+}
+
+// time-domain output of a handle: ISTFT of the separated estimates already sitting on the device as (B, N, F, T) complex64;
+// y (B, N, out_len) float32/float64 on the host
+int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, int hop_size, const double* window, void* y, int dtype) {
+    if (!pow2(fft_size) || fft_size < 8 || fft_size > 16384) return bss_fail(h, BSS_EUNSUPPORTED, "fft_size must be a power of two in [8, 16384]");
+    if (dtype != BSS_F32 && dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "waveforms are float32 or float64");
+    if (fft_size / 2 + 1 != h->F) return bss_fail(h, BSS_EINVAL, "n_bins of the handle must be fft_size / 2 + 1");
+    const int n_frames = h->T;
+    const int out_len = bss_istft_length(n_frames, fft_size, hop_size);
+    if (out_len < 1) return bss_fail(h, BSS_EINVAL, "invalid ISTFT geometry");
+    FftTables t;
+    int rc = make_tables(window, fft_size, h->stream, &t);
+    float* frames = nullptr;
+    void* od = nullptr;
+    const size_t esz = dtype == BSS_F32 ? 4 : 8;
+    if (rc == BSS_OK && (cudaMalloc(&frames, (size_t)n_signals * n_frames * fft_size * sizeof(float)) != cudaSuccess ||
+                         cudaMalloc(&od, (size_t)n_signals * out_len * esz) != cudaSuccess))
+        rc = BSS_ENOMEM;
+    if (rc == BSS_OK) {
+        IstftParams<float2> p{};
+        p.z = z;
+        p.win = t.win;
+        p.tw = t.tw;
+        p.S = n_signals;
+        p.N = fft_size;
+        p.hop = hop_size;
+        p.n_frames = n_frames;
+        p.scale = (float)(t.win_sum / (double)(fft_size / 2));
+        p.frames = frames;
+        const size_t smem = (size_t)fft_size * sizeof(float2);
+        cudaFuncSetAttribute(istft_frames_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid(n_frames, n_signals);
+        istft_frames_kernel<float2><<<grid, fft_threads(fft_size), smem, h->stream>>>(p);
+        const long long n = (long long)n_signals * out_len;
+        if (dtype == BSS_F32)
+            istft_ola_kernel<float><<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(frames, t.win, (float*)od, n_signals, fft_size, hop_size,
+                                                                                  n_frames, out_len);
+        else
+            istft_ola_kernel<double><<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(frames, t.win, (double*)od, n_signals, fft_size,
+                                                                                   hop_size, n_frames, out_len);
+        h->launches += 2;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(y, od, (size_t)n * esz, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = BSS_ECUDA;
+    }
+    if (frames) cudaFree(frames);
+    if (od) cudaFree(od);
+    free_tables(&t);
+    if (rc != BSS_OK) return bss_fail(h, rc, "istft failed");
     return BSS_OK;
 }

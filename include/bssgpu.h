@@ -175,6 +175,10 @@ int bss_separate(bss_handle* h, void* y, int dtype, int apply_projection_back);
 /* same, into a device buffer of complex64 (B,N,F,T) -- used to feed the NCCL gather of a
  * sharded batch without a host round trip */
 int bss_separate_device(bss_handle* h, void* y_device, int apply_projection_back);
+/* the same tail, continued to the time domain on the device: ISTFT (src/transform/stft.py:10-17) of the separated
+ * estimates; y is (B,N,bss_istft_length(n_frames, fft_size, hop_size)) float32/float64 on the host */
+int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int hop_size, const double* window,
+                          int apply_projection_back);
 /* ISS keeps no filter: W = Y X^H (X X^H)^-1 (src/bss/ilrma.py:167-173); result is readable as
  * BSS_STATE_DEMIX_FILTER afterwards */
 int bss_compute_demix_filter(bss_handle* h);

@@ -86,3 +86,27 @@ def test_waveform_feed_equals_spectrogram_feed(cuda_device):
             outs.append(h.separate((B, C, F, T), np.complex128, projection_back=True))
             h.close()
         assert rel(outs[1], outs[0]) < 1e-4
+
+
+def test_waveform_in_waveform_out(cuda_device):
+    """BatchedGaussILRMA.separate_waveforms: STFT, update loop and ISTFT on the device against the host pipeline
+    scipy.stft -> oracle ILRMA -> scipy.istft."""
+    from audio_source_separation_b200.batch import BatchedGaussILRMA
+    from oracle import ilrma as o_ilrma
+    rng = np.random.default_rng(3)
+    B, C, K, n_samples, fft, hop = 2, 2, 2, 6000, 128, 32
+    s = rng.standard_normal((B, C, n_samples)) * np.array([1.0, 0.3])[None, :, None]
+    A = np.array([[1.0, 0.6], [0.4, 1.0]])
+    x = np.einsum('ij,bjt->bit', A, s)
+    X = ss.stft(x, nperseg=fft, noverlap=fft - hop, window='hann')[2]
+    F, T = X.shape[2:]
+    T0, V0 = rng.random((B, C, F, K)), rng.random((B, C, K, T))
+    y = BatchedGaussILRMA(n_basis=K).separate_waveforms(x, fft, hop, iteration=5, basis=T0, activation=V0)
+    W0 = np.tile(np.eye(C, dtype=np.complex128), (F, 1, 1))
+    for b in range(B):
+        Xb = X[b].astype(np.complex64).astype(np.complex128)
+        Y, _, _ = o_ilrma.run(Xb, iteration=5, n_basis=K, W=W0, T=T0[b].astype(np.float32).astype(np.float64),
+                              V=V0[b].astype(np.float32).astype(np.float64), record_loss=False)
+        want = ss.istft(Y, nperseg=fft, noverlap=fft - hop, window='hann')[1]
+        assert y[b].shape == want.shape
+        assert rel(y[b], want) < 1e-3
