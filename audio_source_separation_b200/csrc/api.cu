@@ -309,6 +309,7 @@ static bool graph_capable(const bss_handle* h) {
 int bss_run(bss_handle* h, int n_iter) {
     if (!h || n_iter < 0) return BSS_EINVAL;
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (is_nmf(h->cfg.method)) return nmf_run(h, n_iter, nullptr);   // one cluster launch for the whole loop when it fits
     const int kPerGraph = 2, kWarm = 2, kMinReplays = 4;
     if (n_iter < kWarm + kPerGraph * kMinReplays || !graph_capable(h)) return run_eager(h, n_iter);
     // eager warm-up: every scratch buffer reaches its final size and every kernel attribute is set before the capture
@@ -360,6 +361,12 @@ int bss_run_record(bss_handle* h, int n_iter, double* loss) {
         h->loss_hist_elems = 0;
         BSS_CUDA(h, cudaMalloc(&h->loss_hist, need * sizeof(double)));
         h->loss_hist_elems = need;
+    }
+    if (is_nmf(h->cfg.method)) {
+        BSS_TRY(nmf_run(h, n_iter, h->loss_hist));
+        if (n_iter > 0)
+            BSS_CUDA(h, cudaMemcpyAsync(loss, h->loss_hist, sizeof(double) * h->B * n_iter, cudaMemcpyDeviceToHost, h->stream));
+        return check_flags(h);
     }
     for (int i = 0; i < n_iter; ++i) {
         BSS_TRY(bss_run(h, 1));

@@ -270,6 +270,8 @@ struct NmfMath {
     double loss_eps;
 };
 int launch_nmf_update(bss_handle* h, const NmfMath& m, const double* Z, double* Tm, double* V, int B, int F, int T, int K);
+int launch_nmf_fused(bss_handle* h, const NmfMath& m, const double* Z, double* Tm, double* V, double* loss_hist, int B, int F, int T,
+                     int K, int n_iter, bool* done);
 int launch_nmf_loss(bss_handle* h, const NmfMath& m, const double* Z, const double* Tm, const double* V, double* terms, int B, int F,
                     int T, int K);
 // partitioned ILRMA (kernels_part.cu)

@@ -28,6 +28,7 @@ int mnmf_separate(bss_handle* h, cf* out);
 // single-channel NMF: methods_nmf.cu
 int nmf_allocate(bss_handle* h);
 int nmf_update_once(bss_handle* h);
+int nmf_run(bss_handle* h, int n_iter, double* loss_hist_device);
 int nmf_loss(bss_handle* h);
 
 // STFT feed: kernels_stft.cu

@@ -77,11 +77,26 @@ int nmf_allocate(bss_handle* h) {
     return BSS_OK;
 }
 
-int nmf_update_once(bss_handle* h) {
+int nmf_update_once(bss_handle* h) { return nmf_run(h, 1, nullptr); }
+
+// n_iter updates; with loss_hist (device, [n_iter][B]) the criterion after every update is recorded as well
+// (NMFbase.update, src/algorithm/nmf.py:165-174).  Small problems run as ONE cluster launch for the whole loop.
+int nmf_run(bss_handle* h, int n_iter, double* loss_hist) {
     if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
     NmfMath m;
     BSS_TRY(nmf_math(h, &m));
-    return launch_nmf_update(h, m, h->nz, h->nt, h->nv, h->B, h->F, h->T, h->K);
+    bool done = false;
+    BSS_TRY(launch_nmf_fused(h, m, h->nz, h->nt, h->nv, loss_hist, h->B, h->F, h->T, h->K, n_iter, &done));
+    if (done) return BSS_OK;
+    for (int i = 0; i < n_iter; ++i) {
+        BSS_TRY(launch_nmf_update(h, m, h->nz, h->nt, h->nv, h->B, h->F, h->T, h->K));
+        if (loss_hist) {
+            BSS_TRY(nmf_loss(h));
+            BSS_CUDA(h, cudaMemcpyAsync(loss_hist + (size_t)i * h->B, h->lossbuf + (size_t)h->B * h->F, sizeof(double) * h->B,
+                                        cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    return BSS_OK;
 }
 
 int nmf_loss(bss_handle* h) {

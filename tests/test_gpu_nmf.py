@@ -106,3 +106,26 @@ def test_nmf_argument_errors(cuda_device):
         ISNMF(algorithm='nope')(Z, iteration=1)
     with pytest.raises(AssertionError):
         ISNMF(algorithm='me', domain=1)(Z, iteration=1)
+
+
+@pytest.mark.parametrize('cls_name,kw', [('EUCNMF', {}), ('KLNMF', dict(domain=1.5)), ('ISNMF', dict(algorithm='me')), ('tNMF', dict(nu=50.0)),
+                                         ('CauchyNMF', dict(algorithm='mm_fast'))])
+def test_nmf_cluster_kernel_equals_phase_kernels(cuda_device, monkeypatch, cls_name, kw):
+    """Small problems run as one thread-block-cluster launch for the whole loop (target rows split over 8 CTAs, partial
+    sums exchanged through distributed shared memory); it must agree with the per-phase kernels it replaces, loss history
+    included, for a row count that is not a multiple of the cluster size."""
+    import audio_source_separation_b200.algorithm.nmf as nmf_mod
+    Z = synth.spectrogram(61, 97, seed=11)
+    results = []
+    for no_cluster in (False, True):
+        if no_cluster:
+            monkeypatch.setenv('BSSGPU_NO_CLUSTER', '1')
+        else:
+            monkeypatch.delenv('BSSGPU_NO_CLUSTER', raising=False)
+        np.random.seed(5)
+        model = getattr(nmf_mod, cls_name)(n_basis=3, **kw)
+        T, V = model(Z, iteration=7)
+        model.update_once()                       # single update through the same path
+        results.append((T, V, np.array(model.loss), np.asarray(model.basis)))
+    for a, b in zip(results[0], results[1]):
+        assert np.allclose(a, b, rtol=1e-11, atol=0)
