@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
 // ------------------------------------------------------------------------------------------- weights 1/R
 // iw [B][F][M][Tp]: inverse of the floored variance (no pass over X needed)
 template <int M>
-__global__ void __launch_bounds__(128) mnmf_weights_kernel(const MnArgs a, float* iw, long long n_items, int n_slabs,
+__global__ void __launch_bounds__(128) mnmf_weights_kernel(const MnArgs a, float* iw, long long n_items, int tiled,
                                                           uint32_t scratch_stride) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -474,7 +474,9 @@ __global__ void __launch_bounds__(128) mnmf_weights_kernel(const MnArgs a, float
         mn_variance<M>(a, gs, lam, R);
 #pragma unroll
         for (int m = 0; m < M; ++m)
-            *reinterpret_cast<float2*>(iw + ((size_t)bf * M + m) * a.Tp + t) = rcp2n(floor2(R[m], a.eps));
+            // tiled: block-interleaved like X (rows = M), so that the tensor-core covariance kernel stages a block with one copy
+            *reinterpret_cast<float2*>(iw + (tiled ? (size_t)bf * M * a.Tp + tile_off(M, a.Tp, m, t) : ((size_t)bf * M + m) * a.Tp + t)) =
+                rcp2n(floor2(R[m], a.eps));
     }
 }
 
@@ -789,12 +791,12 @@ int mn_update_scm(bss_handle* h) {
 }
 
 template <int M>
-int mn_weights(bss_handle* h) {
+int mn_weights(bss_handle* h, int tiled) {
     const MnArgs a = mn_args(h);
     const long long n_items = (long long)a.B * a.F;
     const int wpc = 4;
     const uint32_t stride = (uint32_t)round_up((int)mn_scratch_bytes<M>(a.K), 16);
-    mnmf_weights_kernel<M><<<(unsigned)cdiv(n_items, wpc), wpc * 32, (size_t)wpc * stride, h->stream>>>(a, h->iw, n_items, 0, stride);
+    mnmf_weights_kernel<M><<<(unsigned)cdiv(n_items, wpc), wpc * 32, (size_t)wpc * stride, h->stream>>>(a, h->iw, n_items, tiled, stride);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
@@ -851,9 +853,9 @@ int launch_mnmf_scm(bss_handle* h) {
     MN_DISPATCH(h->C, (rc = mn_update_scm<MM_>(h)))
     return rc;
 }
-int launch_mnmf_weights(bss_handle* h) {
+int launch_mnmf_weights(bss_handle* h, int tiled) {
     int rc = BSS_OK;
-    MN_DISPATCH(h->C, (rc = mn_weights<MM_>(h)))
+    MN_DISPATCH(h->C, (rc = mn_weights<MM_>(h, tiled)))
     return rc;
 }
 int launch_mnmf_loss_terms(bss_handle* h) {

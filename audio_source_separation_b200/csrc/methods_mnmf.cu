@@ -70,7 +70,12 @@ int mnmf_update_once(bss_handle* h) {
     BSS_TRY(launch_mnmf_scm(h));
     // update_diagonalizer (:848-888): R is fixed during the sweep over channels, so all M weighted
     // covariances come from one pass and the Gauss-Seidel sweep runs per bin in registers
-    BSS_TRY(launch_mnmf_weights(h));
+    // all M weighted covariances of a bin as one tensor-core contraction (kernels_cov_mma.cu) ...
+    BSS_TRY(launch_mnmf_weights(h, 1));
+    bool on_tensor_cores = false;
+    BSS_TRY(launch_covariance_mma(h, h->X, h->iw, h->U, h->B, h->F, h->C, h->C, h->T, h->Tp, &on_tensor_cores));
+    // ... or, for shapes it does not cover, the CUDA-core kernel with explicit weights
+    if (!on_tensor_cores) BSS_TRY(launch_mnmf_weights(h, 0));
     CovArgs c{};
     c.X = h->X;
     c.U = h->U;
@@ -84,7 +89,7 @@ int mnmf_update_once(bss_handle* h) {
     c.iw = h->iw;
     c.n_sel = h->C;
     for (int i = 0; i < 8; ++i) c.wsel[i] = i;
-    BSS_TRY(launch_covariance(h, c));
+    if (!on_tensor_cores) BSS_TRY(launch_covariance(h, c));
     IpArgs ip{};
     ip.W = h->W;
     ip.Wf = h->Wf;
