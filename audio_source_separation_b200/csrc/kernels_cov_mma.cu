@@ -36,7 +36,7 @@ struct CovMmaParams {
 };
 
 // hi = v rounded to the nearest TF32 (10 mantissa bits; ties away from zero, exactly cvt.rna.tf32.f32 on finite values),
-// lo = the exact remainder v - hi rounded the same way: v = hi + lo up to 2^-21 |v| with errors of either sign.  (Truncating
+// lo = the exact remainder v - hi, left for the tensor core to truncate: v = hi + lo up to 2^-21 |v| with errors of either sign.  (Truncating
 // instead leaves remainders that all carry the sign of v; the tensor core's own truncating adder then accumulates a
 // systematic error that the per-bin solve of an 8 x 8 system amplifies past the 2e-4 parity bound -- measured.)  Integer
 // add-and-mask instead of the cvt instruction, which ptxas expands into a ~5-instruction sequence: with 68 values to split
@@ -44,7 +44,7 @@ struct CovMmaParams {
 __device__ __forceinline__ uint32_t round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
     hi = round_tf32(v);
-    lo = round_tf32(v - __uint_as_float(hi));
+    lo = __float_as_uint(v - __uint_as_float(hi));   // the tensor core ignores the 13 low mantissa bits itself: 2^-21 |v|, either sign
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
