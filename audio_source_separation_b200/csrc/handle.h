@@ -71,7 +71,8 @@ struct bss_handle {
     // FastMNMF
     float* G = nullptr;            // [B][N][F][M]
     float* G2 = nullptr;           // double buffer of G (the spatial update reads all sources of the old one)
-    float* xt = nullptr;           // [B][F][M][Tp] |Q x|^2
+    float* xt = nullptr;           // [B][F][M][Tp] |Q x|^2 (tile layout, rows = M); valid while xt_valid
+    bool xt_valid = false;
     float* mn_acc = nullptr;       // numerator / denominator accumulators
     float* mn_acc2 = nullptr;
     // NMF (fp64 throughout): target [B][F][T], factors [B][F][K] and [B][K][T]
@@ -281,6 +282,7 @@ int launch_part_basis(bss_handle* h);
 int launch_part_act_finish(bss_handle* h, int n_chunks);
 int launch_part_normalize(bss_handle* h);
 // FastMNMF (kernels_mnmf.cu)
+int launch_mnmf_xt(bss_handle* h);
 int launch_mnmf_basis(bss_handle* h);
 int launch_mnmf_act(bss_handle* h);
 int launch_mnmf_scm(bss_handle* h);

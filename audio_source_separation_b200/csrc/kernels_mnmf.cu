@@ -23,6 +23,7 @@ constexpr int MN_NG = 2;       // sources per item of the spatial update
 
 struct MnArgs {
     const cf* X;          // [B][F][M][Tp]
+    const float* xt;      // [B][F][M][Tp] x~ = |Q x|^2 in the block-interleaved tile layout (rows = M), see mnmf_xt_kernel
     const cf* Qf;         // [B][F][M][M]
     const float* G;       // [B][N][F][M]
     const float* basis;   // [B][N][F][K]
@@ -138,6 +139,50 @@ __device__ __forceinline__ void mn_variance(const MnArgs& a, const float* gs, co
 __device__ __forceinline__ float2 floor2(float2 v, float eps) { return make_float2(fmaxf(v.x, eps), fmaxf(v.y, eps)); }
 __device__ __forceinline__ float2 rcp2n(float2 v) { return make_float2(__frcp_rn(v.x), __frcp_rn(v.y)); }
 
+// ------------------------------------------------------------------------------------------- x~ = |Q x|^2
+// Q only changes at the end of an iteration, so the diagonalised power is computed once per iteration (one pass over X)
+// and the three source / spatial-model passes stream x~ (half the bytes of X, no 8 x 8 complex product per frame).
+template <int M>
+__global__ void __launch_bounds__(256, 1) mnmf_xt_kernel(const MnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const MnArgs& a = p.a;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    WarpStream<MN_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next(p.g, a.X, 1);
+        const int bf = st.cons.item;
+        if (st.first_slab()) {
+            __syncwarp();
+            const cf* q = a.Qf + (size_t)bf * M * M;
+            for (int i = lane; i < M * M; i += 32) reinterpret_cast<float2*>(Qs)[i] = __ldg(q + i);
+            __syncwarp();
+        }
+        const cf* xs = st.acquire(p.g);
+        const int nf = st.frames(p.g);
+        const int tbase = st.frame0(p.g);
+        constexpr int MP = (M + 1) & ~1;   // x~ tiles have an even number of rows: every block is a multiple of 16 bytes
+        float* out = p.out_f + (size_t)bf * MP * a.Tp + (size_t)tbase * MP;   // this block of the x~ tile: [MP][nf]
+#pragma unroll 1
+        for (int tt = 2 * lane; tt < nf; tt += 64) {
+            float4 xv[M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
+            float2 xt[M];
+            mn_power<M>(xv, Qs, xt);
+#pragma unroll
+            for (int m = 0; m < M; ++m) *reinterpret_cast<float2*>(out + (size_t)m * nf + tt) = xt[m];
+        }
+        st.release(p.g);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- basis W
 // item = (bin, chunk of MN_KC basis vectors)
 template <int M>
@@ -150,7 +195,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, reinterpret_cast<const cf*>(a.xt), (int)(blockIdx.x * wpc + warp),
              (int)(gridDim.x * wpc), (int)p.n_items, p.per_bin, lane);
     float2 num[MN_NMAX][MN_KC], den[MN_NMAX][MN_KC];
 #pragma unroll
@@ -161,7 +206,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
     int bf = 0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next(p.g, a.X, p.per_bin);
+        st.issue_next(p.g, reinterpret_cast<const cf*>(a.xt), p.per_bin);
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
             k0 = (st.cons.item - bf * p.per_bin) * MN_KC;
@@ -171,15 +216,15 @@ __global__ void __launch_bounds__(256, 1) mnmf_basis_kernel(const MnParams p) {
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
         }
         const cf* xs = st.acquire(p.g);
-        const int nf = st.frames(p.g);
-        const int tbase = st.frame0(p.g);
+        // the stream moves x~ as pairs of floats: st.frames() counts pairs, nf counts frames
+        const int nfp = st.frames(p.g);
+        const int nf = 2 * nfp;
+        const int tbase = 2 * st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
-            float4 xv[M];
-#pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 xt[M];
-            mn_power<M>(xv, Qs, xt);
+#pragma unroll
+            for (int m = 0; m < M; ++m) xt[m] = reinterpret_cast<const float2*>(xs)[m * nfp + (tt >> 1)];
             const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
             float2 lam[MN_NMAX];
             mn_lambda(a, tb, hrow, lam);
@@ -265,8 +310,9 @@ __global__ void __launch_bounds__(128) mnmf_act_partial_kernel(const MnArgs a, f
 #pragma unroll
         for (int kk = 0; kk < MN_KC; ++kk) num[n][kk] = den[n][kk] = make_float2(0.f, 0.f);
     const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tl;
-    const size_t xoff = tile_off(M, a.Tp, 0, tl);
-    const int xlen = (int)(tile_off(M, a.Tp, 1, tl) - xoff);
+    constexpr int MP = (M + 1) & ~1;   // rows of an x~ tile (see mnmf_xt_kernel)
+    const size_t xoff = tile_off(MP, a.Tp, 0, tl);
+    const int xlen = (int)(tile_off(MP, a.Tp, 1, tl) - xoff);
     const int f_begin = chunk * bins_per_chunk;
     const int f_end = min(a.F, f_begin + bins_per_chunk);
 #pragma unroll 1
@@ -274,12 +320,10 @@ __global__ void __launch_bounds__(128) mnmf_act_partial_kernel(const MnArgs a, f
         const long long bf = (long long)b * a.F + f;
         __syncwarp();
         mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
-        float4 xv[M];
-#pragma unroll
-        for (int c = 0; c < M; ++c)
-            xv[c] = live ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)bf * M * a.Tp + xoff + (size_t)c * xlen)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float2 xt[M];
-        mn_power<M>(xv, Qs, xt);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            xt[m] = live ? __ldg(reinterpret_cast<const float2*>(a.xt + (size_t)bf * MP * a.Tp + xoff + (size_t)m * xlen)) : make_float2(0.f, 0.f);
         float2 lam[MN_NMAX];
         mn_lambda(a, tb, hrow, lam);
         float2 R[M];
@@ -361,7 +405,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, reinterpret_cast<const cf*>(a.xt), (int)(blockIdx.x * wpc + warp),
              (int)(gridDim.x * wpc), (int)p.n_items, p.per_bin, lane);
     float2 A[MN_NMAX][MN_MG], Bq[MN_NMAX][MN_MG];
 #pragma unroll
@@ -372,7 +416,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     int bf = 0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next(p.g, a.X, p.per_bin);
+        st.issue_next(p.g, reinterpret_cast<const cf*>(a.xt), p.per_bin);
         if (st.first_slab()) {
             bf = st.cons.item / p.per_bin;
             m0 = (st.cons.item - bf * p.per_bin) * MN_MG;
@@ -382,13 +426,12 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
             mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
         }
         const cf* xs = st.acquire(p.g);
-        const int nf = st.frames(p.g);
-        const int tbase = st.frame0(p.g);
+        // the stream moves x~ as pairs of floats: st.frames() counts pairs, nf counts frames
+        const int nfp = st.frames(p.g);
+        const int nf = 2 * nfp;
+        const int tbase = 2 * st.frame0(p.g);
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
-            float4 xv[M];
-#pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             const float* hrow = a.act + (size_t)b * a.N * a.K * a.Tp + tbase + tt;
             float2 lam[MN_NMAX];
             mn_lambda(a, tb, hrow, lam);
@@ -396,19 +439,7 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
 #pragma unroll
             for (int j = 0; j < MN_MG; ++j) {
                 const int m = min(m0 + j, M - 1);
-                float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < M; ++c) {
-                    const float2 w = reinterpret_cast<const float2*>(Qs)[m * M + c];
-                    const float2 x0 = make_float2(xv[c].x, xv[c].y), x1 = make_float2(xv[c].z, xv[c].w);
-                    const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
-                    y0 = __ffma2_rn(x0, wx, y0);
-                    y0 = __ffma2_rn(make_float2(-x0.y, x0.x), wy, y0);
-                    y1 = __ffma2_rn(x1, wx, y1);
-                    y1 = __ffma2_rn(make_float2(-x1.y, x1.x), wy, y1);
-                }
-                const float2 s0 = __fmul2_rn(y0, y0), s1 = __fmul2_rn(y1, y1);
-                const float2 xt = make_float2(s0.x + s0.y, s1.x + s1.y);
+                const float2 xt = reinterpret_cast<const float2*>(xs)[m * nfp + (tt >> 1)];
                 float2 r = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int n = 0; n < MN_NMAX; ++n)
@@ -492,13 +523,13 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
     mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
     WarpStream<MN_STAGES> st;
     st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
-             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, a.X, (int)(blockIdx.x * wpc + warp),
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, reinterpret_cast<const cf*>(a.xt), (int)(blockIdx.x * wpc + warp),
              (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
     double total = 0.0;
     int b = 0, f = 0;
 #pragma unroll 1
     while (st.active()) {
-        st.issue_next(p.g, a.X, 1);
+        st.issue_next(p.g, reinterpret_cast<const cf*>(a.xt), 1);
         const int bf = st.cons.item;
         if (st.first_slab()) {
             b = bf / a.F;
@@ -508,16 +539,16 @@ __global__ void __launch_bounds__(256, 1) mnmf_loss_kernel(const MnParams p) {
             total = 0.0;
         }
         const cf* xs = st.acquire(p.g);
-        const int nf = st.frames(p.g);
-        const int tbase = st.frame0(p.g);
+        // the stream moves x~ as pairs of floats: st.frames() counts pairs, nf counts frames
+        const int nfp = st.frames(p.g);
+        const int nf = 2 * nfp;
+        const int tbase = 2 * st.frame0(p.g);
         float part = 0.f;
 #pragma unroll 1
         for (int tt = 2 * lane; tt < nf; tt += 64) {
-            float4 xv[M];
-#pragma unroll
-            for (int c = 0; c < M; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * nf + tt);
             float2 xt[M];
-            mn_power<M>(xv, Qs, xt);
+#pragma unroll
+            for (int m = 0; m < M; ++m) xt[m] = reinterpret_cast<const float2*>(xs)[m * nfp + (tt >> 1)];
             const int t = tbase + tt;
             float2 lam[MN_NMAX];
             mn_lambda(a, tb, a.act + (size_t)b * a.N * a.K * a.Tp + t, lam);
@@ -694,9 +725,16 @@ __global__ void __launch_bounds__(256) mnmf_norm_basis_kernel(float* basis, floa
     for (int t = threadIdx.x; t < Tp; t += blockDim.x) hh[t] = (float)((double)hh[t] * om);
 }
 
+// f32_tiles: the kernel streams x~ (float tiles) as pairs of floats: rows of Tp / 2 pairs, 64-pair blocks
 template <int M, typename Kern>
-int launch_stream(bss_handle* h, Kern kern, MnParams& p, int per_bin, int slab, int max_wpc) {
+int launch_stream(bss_handle* h, Kern kern, MnParams& p, int per_bin, int slab, int max_wpc, bool f32_tiles = true) {
     p.g = make_tile_geom(M, p.a.Tp, slab);
+    if (f32_tiles) {
+        p.g.n_rows = (M + 1) & ~1;
+        p.g.row_len = p.a.Tp / 2;
+        p.g.slab = p.g.n_slabs == 1 ? p.g.row_len : BSS_XSLAB / 2;
+        p.g.stage_bytes = (uint32_t)(((size_t)p.g.n_rows * p.g.slab * 8 + 127) / 128 * 128);
+    }
     p.per_bin = per_bin;
     p.n_items = (long long)p.a.B * p.a.F * per_bin;
     StreamPlan sp;
@@ -715,6 +753,7 @@ int launch_stream(bss_handle* h, Kern kern, MnParams& p, int per_bin, int slab, 
 MnArgs mn_args(bss_handle* h) {
     MnArgs a{};
     a.X = h->X;
+    a.xt = h->xt;
     a.Qf = h->Wf;
     a.G = h->G;
     a.basis = h->basis;
@@ -728,6 +767,14 @@ MnArgs mn_args(bss_handle* h) {
     a.K = h->K;
     a.eps = (float)h->cfg.eps;
     return a;
+}
+
+template <int M>
+int mn_xt(bss_handle* h) {
+    MnParams p{};
+    p.a = mn_args(h);
+    p.out_f = h->xt;
+    return launch_stream<M>(h, mnmf_xt_kernel<M>, p, 1, MN_SLAB, 8, false);
 }
 
 template <int M>
@@ -821,7 +868,7 @@ int mn_separate(bss_handle* h, cf* out) {
     p.a = mn_args(h);
     p.out_c = out;
     p.qinv = qinv;
-    return launch_stream<M>(h, mnmf_separate_kernel<M>, p, 1, MN_SLAB, 8);
+    return launch_stream<M>(h, mnmf_separate_kernel<M>, p, 1, MN_SLAB, 8, false);
 }
 
 }  // namespace
@@ -838,6 +885,11 @@ int mn_separate(bss_handle* h, cf* out) {
         default: return bss_fail(h, BSS_EINVAL, "n_channels must be between 2 and 8"); \
     }
 
+int launch_mnmf_xt(bss_handle* h) {
+    int rc = BSS_OK;
+    MN_DISPATCH(h->C, (rc = mn_xt<MM_>(h)))
+    return rc;
+}
 int launch_mnmf_basis(bss_handle* h) {
     int rc = BSS_OK;
     MN_DISPATCH(h->C, (rc = mn_update_basis<MM_>(h)))

@@ -33,6 +33,7 @@ int mnmf_allocate(bss_handle* h) {
     BSS_TRY(dalloc(h, &h->basis2, B * N * F * K));
     BSS_TRY(dalloc(h, &h->act, B * N * K * Tp));
     BSS_TRY(dalloc(h, &h->iw, B * F * M * Tp));
+    BSS_TRY(dalloc(h, &h->xt, B * F * ((M + 1) / 2 * 2) * Tp));   // x~ tiles have an even number of rows
     return BSS_OK;
 }
 
@@ -63,6 +64,8 @@ int mnmf_reset(bss_handle* h) {
 int mnmf_update_once(bss_handle* h) {
     if (h->cfg.normalize != BSS_NORMALIZE_NONE && h->cfg.normalize != BSS_NORMALIZE_POWER)
         return bss_fail(h, BSS_EINVAL, "Not support normalization based on projection-back. Choose 'power'");   // mnmf.py:772-773
+    // x~ = |Q x|^2 once per iteration: Q only changes in update_diagonalizer below
+    BSS_TRY(launch_mnmf_xt(h));
     // update_NMF (mnmf.py:775-815)
     BSS_TRY(launch_mnmf_basis(h));
     BSS_TRY(launch_mnmf_act(h));
@@ -115,6 +118,7 @@ int mnmf_loss(bss_handle* h) {
     double* result = h->lossbuf + BF;
     BSS_CUDA(h, cudaMemsetAsync(result, 0, sizeof(double) * h->B, h->stream));
     BSS_TRY(launch_logdet(h, h->W, h->logdet, (long long)BF, h->C, 1));
+    BSS_TRY(launch_mnmf_xt(h));
     BSS_TRY(launch_mnmf_loss_terms(h));
     return launch_loss_finish(h, h->lossbuf, h->logdet, (double)h->T, h->B, h->F, result);
 }
