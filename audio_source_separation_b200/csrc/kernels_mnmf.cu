@@ -10,6 +10,8 @@
 //   spatial g    per-bin reduction over frames            mnmf.py:832-844
 //   weights 1/R  for the diagonaliser's covariances       mnmf.py:867-868
 //   normalise    mnmf.py:753-767,  loss :890-917,  separate (multichannel Wiener filter) :919-946
+#include <cstdlib>
+
 #include "handle.h"
 #include "smallmat.cuh"
 
@@ -485,6 +487,118 @@ __global__ void __launch_bounds__(256, 1) mnmf_scm_kernel(const MnParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------- spatial g on tensor cores
+// The same update as one small contraction per bin:  A[n][m] = sum_t Lambda[n,t] u[m,t],  B[n][m] = sum_t Lambda[n,t] / R[m,t]
+// with u = x~ / R^2: two [8 x T] x [T x 8] products sharing their left operand.  One warp per bin, mma.sync.m16n8k8 (3xTF32),
+// K = 8 frames per step: lane (g, tig) computes Lambda of source g and u, 1/R of channel g at frames tig and tig + 4 (the
+// Lambda of the other sources, needed for R, come by shuffle), i.e. exactly its own fragment entries; the D fragments hold
+// A[g][2 tig .. 2 tig + 1] and B[g][..], from which the lane updates its two entries of g.  11 warp instructions per frame
+// instead of 41 for the CUDA-core kernel above (kept for reference and for BSSGPU_NO_MMA).
+__device__ __forceinline__ uint32_t mn_round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void mn_split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = mn_round_tf32(v);
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mn_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int M>
+__global__ void __launch_bounds__(512, 1) mnmf_scm_mma_kernel(const MnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const MnArgs& a = p.a;
+    float *Qs, *gs, *tb, *red;
+    mn_scratch<M>(reinterpret_cast<float*>(smem + p.scratch_off + (size_t)warp * p.scratch_stride), a.N, a.K, Qs, gs, tb, red);
+    WarpStream<MN_STAGES> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MN_STAGES,
+             smem + p.ring_off + (size_t)warp * MN_STAGES * p.g.stage_bytes, reinterpret_cast<const cf*>(a.xt),
+             (int)(blockIdx.x * wpc + warp), (int)(gridDim.x * wpc), (int)p.n_items, 1, lane);
+    const bool n_live = g < a.N, m_live = g < M;
+    float dA[4], dAc[4], dB[4], dBc[4];
+    int b = 0, f = 0;
+#pragma unroll 1
+    while (st.active()) {
+        st.issue_next(p.g, reinterpret_cast<const cf*>(a.xt), 1);
+        const int bf = st.cons.item;
+        if (st.first_slab()) {
+            b = bf / a.F;
+            f = bf - b * a.F;
+            __syncwarp();
+            mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dA[q] = dAc[q] = dB[q] = dBc[q] = 0.f;
+        }
+        const float* xs = reinterpret_cast<const float*>(st.acquire(p.g));
+        const int nf = 2 * st.frames(p.g);          // frames of this block
+        const int tbase = 2 * st.frame0(p.g);
+        const float* hrow = a.act + ((size_t)b * a.N + (n_live ? g : 0)) * a.K * a.Tp + tbase;
+#pragma unroll 1
+        for (int k0 = 0; k0 < nf; k0 += 8) {
+            const int tA = k0 + tig, tB = tA + 4;
+            const bool lA = tA < nf, lB = tB < nf;
+            // Lambda of this lane group's source at its two frames
+            float lamA = 0.f, lamB = 0.f;
+            if (n_live) {
+                for (int k = 0; k < a.K; ++k) {
+                    const float tk = tb[g * a.K + k];
+                    if (lA) lamA = fmaf(tk, __ldg(hrow + (size_t)k * a.Tp + tA), lamA);
+                    if (lB) lamB = fmaf(tk, __ldg(hrow + (size_t)k * a.Tp + tB), lamB);
+                }
+            }
+            // R of this lane group's channel: the other sources' Lambda come from lanes (n, tig)
+            float RA = 0.f, RB = 0.f;
+#pragma unroll
+            for (int n = 0; n < MN_NMAX; ++n) {
+                const float la = __shfl_sync(BSS_FULL, lamA, n * 4 + tig);
+                const float lb = __shfl_sync(BSS_FULL, lamB, n * 4 + tig);
+                if (n < a.N && m_live) {
+                    const float gg = gs[n * M + g];
+                    RA = fmaf(la, gg, RA);
+                    RB = fmaf(lb, gg, RB);
+                }
+            }
+            const float riA = __frcp_rn(fmaxf(RA, a.eps)), riB = __frcp_rn(fmaxf(RB, a.eps));
+            const float xA = (m_live && lA) ? xs[g * nf + tA] : 0.f;
+            const float xB = (m_live && lB) ? xs[g * nf + tB] : 0.f;
+            const float uA = xA * riA * riA, uB = xB * riB * riB;
+            uint32_t ah[4], al[4], uh[2], ul[2], rh[2], rl[2];
+            mn_split_tf32(lamA, ah[0], al[0]);
+            mn_split_tf32(lamB, ah[2], al[2]);
+            ah[1] = ah[3] = al[1] = al[3] = 0u;
+            mn_split_tf32(uA, uh[0], ul[0]);
+            mn_split_tf32(uB, uh[1], ul[1]);
+            mn_split_tf32((m_live && lA) ? riA : 0.f, rh[0], rl[0]);
+            mn_split_tf32((m_live && lB) ? riB : 0.f, rh[1], rl[1]);
+            mn_mma_tf32(dAc, al, uh);
+            mn_mma_tf32(dBc, al, rh);
+            mn_mma_tf32(dAc, ah, ul);
+            mn_mma_tf32(dBc, ah, rl);
+            mn_mma_tf32(dA, ah, uh);
+            mn_mma_tf32(dB, ah, rh);
+        }
+        if (st.last_slab(p.g)) {
+            // c0, c1 = rows n = g, columns m = 2 tig, 2 tig + 1
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int m = 2 * tig + h2;
+                if (n_live && m < M) {
+                    const float av = dA[h2] + dAc[h2];
+                    const float bv = fmaxf(dB[h2] + dBc[h2], a.eps);
+                    const size_t idx = (((size_t)b * a.N + g) * a.F + f) * M + m;
+                    p.out_f[idx] = a.G[idx] * sqrtf(av / bv);
+                }
+            }
+        }
+        st.release(p.g);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- weights 1/R
 // iw [B][F][M][Tp]: inverse of the floored variance (no pass over X needed)
 template <int M>
@@ -830,7 +944,10 @@ int mn_update_scm(bss_handle* h) {
     MnParams p{};
     p.a = mn_args(h);
     p.out_f = h->G2;
-    BSS_TRY((launch_stream<M>(h, mnmf_scm_kernel<M>, p, (int)cdiv(M, MN_MG), MN_SLAB, 8)));
+    if (getenv("BSSGPU_NO_MMA"))
+        BSS_TRY((launch_stream<M>(h, mnmf_scm_kernel<M>, p, (int)cdiv(M, MN_MG), MN_SLAB, 8)));
+    else
+        BSS_TRY((launch_stream<M>(h, mnmf_scm_mma_kernel<M>, p, 1, MN_SLAB, 16)));
     float* t = h->G;
     h->G = h->G2;
     h->G2 = t;
