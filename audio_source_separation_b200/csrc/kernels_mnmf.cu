@@ -606,13 +606,26 @@ __global__ void __launch_bounds__(128) mnmf_weights_kernel(const MnArgs a, float
                                                           uint32_t scratch_stride) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long bf = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (bf >= n_items) return;
-    const int b = (int)(bf / a.F), f = bf - b * a.F;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + warp;   // (bin, 128-frame block)
+    if (item >= n_items) return;
+    const int n_blocks = (a.Tp + BSS_XSLAB - 1) / BSS_XSLAB;
+    const long long bf = item / n_blocks;
+    const int blk = (int)(item - bf * n_blocks);
+    const int b = (int)(bf / a.F), f = (int)(bf - (long long)b * a.F);
     float *Qs, *gs, *tb, *red;
     mn_scratch<M>(reinterpret_cast<float*>(smem + (size_t)warp * scratch_stride), a.N, a.K, Qs, gs, tb, red);
-    mn_load_bin<M>(a, bf, b, f, Qs, gs, tb, lane);
-    for (int t = 2 * lane; t < a.Tp; t += 64) {
+    // only g and the basis row are needed here
+    for (int i = lane; i < a.N * M; i += 32) {
+        const int n = i / M, m = i - n * M;
+        gs[i] = __ldg(a.G + (((size_t)b * a.N + n) * a.F + f) * M + m);
+    }
+    for (int i = lane; i < a.N * a.K; i += 32) {
+        const int n = i / a.K, k = i - n * a.K;
+        tb[i] = __ldg(a.basis + (((size_t)b * a.N + n) * a.F + f) * a.K + k);
+    }
+    __syncwarp();
+    const int t_end = min(a.Tp, (blk + 1) * BSS_XSLAB);
+    for (int t = blk * BSS_XSLAB + 2 * lane; t < t_end; t += 64) {
         float2 lam[MN_NMAX];
         mn_lambda(a, tb, a.act + (size_t)b * a.N * a.K * a.Tp + t, lam);
         float2 R[M];
@@ -780,19 +793,20 @@ __global__ void __launch_bounds__(64) mnmf_qinv_kernel(const double2* Qg, cf* ou
 
 // ------------------------------------------------------------------------------------------- normalisation
 // per bin: s = max(mean_m sum_c |Q[m][c]|^2, eps); Q /= sqrt(s); g /= s; gamma[n] = max(sum_m g, eps); g /= gamma;
-// W[n,f,:] *= gamma          mnmf.py:753-762
+// W[n,f,:] *= gamma          mnmf.py:753-762.  One warp per bin (fp64, fixed-order lane reductions).
 __global__ void __launch_bounds__(128) mnmf_norm_bin_kernel(double2* Q, cf* Qf, float* G, float* basis, int B, int N, int F, int M,
                                                            int K, double eps) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (idx >= (long long)B * F) return;
     const int b = (int)(idx / F), f = (int)(idx - (long long)b * F);
     double2* q = Q + (size_t)idx * M * M;
     double s = 0.0;
-    for (int i = 0; i < M * M; ++i) s += q[i].x * q[i].x + q[i].y * q[i].y;
-    s /= (double)M;
+    for (int i = lane; i < M * M; i += 32) s += q[i].x * q[i].x + q[i].y * q[i].y;
+    s = warp_sum(s) / (double)M;
     if (s < eps) s = eps;
     const double is = 1.0 / sqrt(s);
-    for (int i = 0; i < M * M; ++i) {
+    for (int i = lane; i < M * M; i += 32) {
         double2 v = q[i];
         v.x *= is;
         v.y *= is;
@@ -801,16 +815,12 @@ __global__ void __launch_bounds__(128) mnmf_norm_bin_kernel(double2* Q, cf* Qf, 
     }
     for (int n = 0; n < N; ++n) {
         float* g = G + (((size_t)b * N + n) * F + f) * M;
-        double gv[8];
-        double sum = 0.0;
-        for (int m = 0; m < M; ++m) {
-            gv[m] = (double)g[m] / s;
-            sum += gv[m];
-        }
+        const double gv = lane < M ? (double)g[lane] / s : 0.0;
+        double sum = warp_sum(gv);
         if (sum < eps) sum = eps;
-        for (int m = 0; m < M; ++m) g[m] = (float)(gv[m] / sum);
+        if (lane < M) g[lane] = (float)(gv / sum);
         float* w = basis + (((size_t)b * N + n) * F + f) * K;
-        for (int k = 0; k < K; ++k) w[k] = (float)((double)w[k] * sum);
+        for (int k = lane; k < K; k += 32) w[k] = (float)((double)w[k] * sum);
     }
 }
 
@@ -957,7 +967,7 @@ int mn_update_scm(bss_handle* h) {
 template <int M>
 int mn_weights(bss_handle* h, int tiled) {
     const MnArgs a = mn_args(h);
-    const long long n_items = (long long)a.B * a.F;
+    const long long n_items = (long long)a.B * a.F * ((a.Tp + BSS_XSLAB - 1) / BSS_XSLAB);
     const int wpc = 4;
     const uint32_t stride = (uint32_t)round_up((int)mn_scratch_bytes<M>(a.K), 16);
     mnmf_weights_kernel<M><<<(unsigned)cdiv(n_items, wpc), wpc * 32, (size_t)wpc * stride, h->stream>>>(a, h->iw, n_items, tiled, stride);
@@ -1039,7 +1049,7 @@ int launch_mnmf_separate(bss_handle* h, cf* out) {
 }
 int launch_mnmf_normalize(bss_handle* h) {
     const long long n_bins = (long long)h->B * h->F;
-    mnmf_norm_bin_kernel<<<(unsigned)cdiv(n_bins, 128), 128, 0, h->stream>>>(h->W, h->Wf, h->G, h->basis, h->B, h->N, h->F, h->C, h->K,
+    mnmf_norm_bin_kernel<<<(unsigned)cdiv(n_bins, 4), 128, 0, h->stream>>>(h->W, h->Wf, h->G, h->basis, h->B, h->N, h->F, h->C, h->K,
                                                                             h->cfg.eps);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
