@@ -443,3 +443,22 @@ class RegularizedILRMA(ILRMAbase):
         super().__init__(n_basis=n_basis, partitioning=partitioning, normalize=normalize, algorithm_spatial=algorithm_spatial,
                          callbacks=callbacks, recordable_loss=recordable_loss, eps=eps)
         raise NotImplementedError("In progress")
+
+
+def update_spatial_model_ip(input, demix_filter, variance, threshold=THRESHOLD, eps=EPS):
+    """One iterative-projection sweep with externally supplied source variances, the spatial half of every determined
+    method of the reference: `GaussILRMA.update_spatial_model_ip` (src/bss/ilrma.py:483-535) once R = (T V)^(2/domain) is
+    known, and verbatim `GaussIDLMA.update_space_model` (src/sss/idlma.py:175-210), whose R comes from a DNN.
+
+    Args:
+        input (n_channels, n_bins, n_frames): mixture
+        demix_filter (n_bins, n_sources, n_channels): current filters
+        variance (n_sources, n_bins, n_frames): source variances R (floored at `eps` here, as the reference does)
+    Returns:
+        demix_filter (n_bins, n_sources, n_channels), estimation (n_sources, n_bins, n_frames)
+    """
+    R = np.array(variance, dtype=np.float64, copy=True)
+    R[R < eps] = eps
+    U = _lib.weighted_covariance(input, R)
+    W, _ = _lib.ip_update(demix_filter, U, threshold=threshold)
+    return W, _lib.demix(input, W)

@@ -382,3 +382,21 @@ def test_all_zero_bin_raises_linalgerror(cuda_device):
     X[:, 4, :] = 0
     with pytest.raises(np.linalg.LinAlgError):
         AuxLaplaceIVA(recordable_loss=False)(X, iteration=2)
+
+
+def test_update_spatial_model_ip_with_external_variances(cuda_device):
+    """The spatial update as a stand-alone operator (what GaussIDLMA.update_space_model, src/sss/idlma.py:175-210, runs with
+    DNN variances): covariance + IP sweep + demixing from the stateless C entry points."""
+    from audio_source_separation_b200.bss.ilrma import update_spatial_model_ip
+    C, F, T = 3, 21, 70
+    X = synth.mix2(C, F, T, seed=9)
+    rng = np.random.default_rng(4)
+    R = 10 ** rng.uniform(-3, 1, size=(C, F, T))
+    R[0, 0, :5] = 0.0                                   # exercises the eps floor
+    W0 = synth.random_demix(C, F, seed=2)
+    W, Y = update_spatial_model_ip(X, W0, R)
+    Rf = np.maximum(R, 1e-12)
+    Wo = W0.copy()
+    core.ip_rows(Wo, core.weighted_covariance(X, Rf))
+    assert rel(W, Wo) < 1e-4
+    assert rel(Y, core.demix(X, Wo)) < 1e-4
