@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(COV_MAX_WARPS * 32, 1) cov_kernel(const CovPar
     // a CTA walks the contiguous item range [lo, hi); its warps interleave inside it
     int lo, hi;
     cta_item_range((int)p.n_items, lo, hi);
-    WarpStream<COV_STAGES> st;
-    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * COV_STAGES,
-             smem + p.ring_off + (size_t)warp * COV_STAGES * p.g.stage_bytes, a.X, lo + warp, wpc, hi, p.n_groups, lane);
+    // without the shared-memory cache the activation rows are read through L1: a two-stage ring leaves L1 room for them
+    constexpr int STG = (WM == WM_ILRMA && !CACHE) ? 2 : COV_STAGES;
+    WarpStream<STG> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * STG,
+             smem + p.ring_off + (size_t)warp * STG * p.g.stage_bytes, a.X, lo + warp, wpc, hi, p.n_groups, lane);
     const float* vcache = reinterpret_cast<const float*>(smem + p.cache_off);
     int b_lo = 0;
     if (CACHE) b_lo = load_act_cache(reinterpret_cast<float*>(smem + p.cache_off), a.act, a.NW * K * Tp, lo, hi, p.n_groups, a.F);
@@ -265,7 +267,7 @@ int launch_cov_t(bss_handle* h, const CovArgs& a) {
         p.ring_off = sp.ring_off;
         return launch_cov_c<C, NS, WM, KT, POW, true>(h, p, sp, smem_bytes);
     }
-    if (!plan_stream(h, p.g, COV_STAGES, scratch, (int)p.n_items, COV_MAX_WARPS, &sp))
+    if (!plan_stream(h, p.g, WM == WM_ILRMA ? 2 : COV_STAGES, scratch, (int)p.n_items, COV_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "covariance: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;

@@ -105,9 +105,11 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
     float* red = tb + (KFIX ? 0 : N * K);                                                           // [MP]
     int lo, hi;
     cta_item_range((int)p.n_items, lo, hi);
-    WarpStream<MU_STAGES> st;
-    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * MU_STAGES,
-             smem + p.ring_off + (size_t)warp * MU_STAGES * p.g.stage_bytes, FROM_Y ? a.Y : a.X, lo + warp, wpc, hi, p.n_kc, lane);
+    // without the shared-memory cache the activation rows are read through L1: a two-stage ring leaves L1 room for them
+    constexpr int STG = CACHE ? MU_STAGES : 2;
+    WarpStream<STG> st;
+    st.start(p.g, reinterpret_cast<uint64_t*>(smem) + warp * STG,
+             smem + p.ring_off + (size_t)warp * STG * p.g.stage_bytes, FROM_Y ? a.Y : a.X, lo + warp, wpc, hi, p.n_kc, lane);
     const float* vcache = reinterpret_cast<const float*>(smem + p.cache_off);
     int b_lo = 0;
     if (CACHE) b_lo = load_act_cache(reinterpret_cast<float*>(smem + p.cache_off), a.act, N * K * Tp, lo, hi, p.n_kc, a.F);
@@ -259,7 +261,7 @@ int launch_mu_basis_t(bss_handle* h, const MuArgs& a) {
     size_t smem_bytes = 0;
     const bool cached = plan_stream_cached(h, p.g, MU_STAGES, scratch, p.n_items, MU_MAX_WARPS, (size_t)C * a.K * a.Tp * sizeof(float),
                                            (long long)a.F * p.n_kc, &sp, &p.cache_off, &smem_bytes);
-    if (!cached && !plan_stream(h, p.g, MU_STAGES, scratch, p.n_items, MU_MAX_WARPS, &sp))
+    if (!cached && !plan_stream(h, p.g, 2, scratch, p.n_items, MU_MAX_WARPS, &sp))
         return bss_fail(h, BSS_EINVAL, "source model: frame tile does not fit in shared memory");
     p.scratch_off = sp.scratch_off;
     p.scratch_stride = sp.scratch_stride;
