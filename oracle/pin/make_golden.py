@@ -27,12 +27,12 @@ warnings.simplefilter('ignore')
 
 from bss.ilrma import GaussILRMA, tILRMA  # noqa: E402
 from bss.iva import AuxLaplaceIVA, AuxGaussIVA  # noqa: E402
-from bss.mnmf import FastMultichannelISNMF  # noqa: E402
+from bss.mnmf import FastMultichannelISNMF, MultichannelISNMF  # noqa: E402
 from algorithm.nmf import EUCNMF, KLNMF, ISNMF, tNMF, CauchyNMF  # noqa: E402
 from algorithm.projection_back import projection_back  # noqa: E402
 from utils.utils_linalg import parallel_sort  # noqa: E402
 
-from oracle import core, ilrma, auxiva, fastmnmf, nmf, synth  # noqa: E402
+from oracle import core, ilrma, auxiva, fastmnmf, mnmf, nmf, synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 TOL = 1e-9
@@ -146,6 +146,40 @@ def case_fastmnmf(name, M, N, F, T, K, iters):
                  'spatial_covariance': st['G'], 'loss': np.array(o_loss)}, want)
     save(name, dict(model='FastMNMF', n_basis=K, n_sources=N, iteration=iters),
          {'X': X, 'W0': W0, 'H0': H0}, want)
+
+
+# ------------------------------------------------------------------------------- Sawada IS-MNMF
+
+def mnmf_initial_state(C, N, F, T, K, seed=5):
+    """Random Hermitian positive-definite spatial covariances of unit trace, latent columns summing to one."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((F, N, C, C)) + 1j * rng.standard_normal((F, N, C, C))
+    H0 = A @ A.swapaxes(-1, -2).conj() + 0.5 * np.eye(C)
+    H0 = H0 / np.trace(H0, axis1=-2, axis2=-1).real[..., None, None]
+    H0 = (H0 + H0.swapaxes(-1, -2).conj()) / 2
+    Z0 = rng.random((N, K)) + 0.5
+    Z0 = Z0 / Z0.sum(axis=0)
+    T0 = rng.random((F, K)) + 0.1
+    V0 = rng.random((K, T)) + 0.1
+    return H0, Z0, T0, V0
+
+
+def case_mnmf_sawada(name, C, N, F, T, K, iters, normalize=True, identity_spatial=False):
+    X = synth.mix2(C, F, T, K=2, seed=4)
+    H0, Z0, T0, V0 = mnmf_initial_state(C, N, F, T, K)
+    if identity_spatial:
+        H0 = np.tile(np.eye(C), (F, N, 1, 1)).astype(np.complex128)
+    model = MultichannelISNMF(n_basis=K, n_sources=N, normalize=normalize)
+    out = model(X, iteration=iters, spatial=H0, latent=Z0, basis=T0, activation=V0)
+    want = {'output': out, 'spatial': model.spatial, 'latent': model.latent, 'basis': model.basis,
+            'activation': model.activation, 'loss': np.array(model.loss)}
+    for riccati in (mnmf.solve_riccati, mnmf.solve_riccati_hermitian):
+        o_out, st, o_loss = mnmf.run(X, iteration=iters, n_basis=K, n_sources=N, normalize=normalize, riccati=riccati,
+                                     H=H0, Z=Z0, T=T0, V=V0)
+        check(name, {'output': o_out, 'spatial': st['H'], 'latent': st['Z'], 'basis': st['T'], 'activation': st['V'],
+                     'loss': np.array(o_loss)}, want, tol=1e-8)
+    save(name, dict(model='MultichannelISNMF', n_basis=K, n_sources=N, normalize=normalize, iteration=iters),
+         {'X': X, 'H0': H0, 'Z0': Z0, 'T0': T0, 'V0': V0}, want)
 
 
 # ------------------------------------------------------------------------------- NMF
@@ -288,6 +322,9 @@ def main():
     case_auxiva('auxiva_laplace_ip2', 'laplace', 3, 17, 40, 'IP2', 4)
     case_fastmnmf('fastmnmf_m3n3', 3, 3, 17, 40, 2, 3)
     case_fastmnmf('fastmnmf_m4n2', 4, 2, 9, 32, 3, 2)
+    case_mnmf_sawada('mnmf_sawada_c2n2', 2, 2, 9, 24, 3, 3)
+    case_mnmf_sawada('mnmf_sawada_c3n2', 3, 2, 7, 20, 2, 2, normalize=False)
+    case_mnmf_sawada('mnmf_sawada_c4n3_eye', 4, 3, 5, 16, 3, 3, identity_spatial=True)
     case_nmf('nmf_euc_d2', 'euc', 33, 24, 4, 5, domain=2)
     case_nmf('nmf_euc_d1', 'euc', 33, 24, 4, 5, domain=1)
     case_nmf('nmf_kl_d2', 'kl', 33, 24, 4, 5, domain=2)

@@ -118,3 +118,23 @@ def test_stft_fixture_matches_scipy():
     assert rel(Z, o['stft']) < 1e-14
     y = ss.istft(Z, nperseg=n, noverlap=n - h, window='hann')[1][..., :meta['n_samples']]
     assert rel(y, o['istft']) < 1e-12
+
+
+MNMF_SAWADA_CASES = ['mnmf_sawada_c2n2', 'mnmf_sawada_c3n2', 'mnmf_sawada_c4n3_eye']
+
+
+@pytest.mark.parametrize('name', MNMF_SAWADA_CASES)
+@pytest.mark.parametrize('closed_form', [False, True])
+def test_mnmf_sawada(name, closed_form):
+    """Sawada IS-MNMF against the reference fixtures, with the reference's 2M x 2M eigen Riccati solver and with the
+    Hermitian closed form the CUDA path uses."""
+    from oracle import mnmf
+    meta, i, o = load_golden(name)
+    riccati = mnmf.solve_riccati_hermitian if closed_form else mnmf.solve_riccati
+    out, st, loss = mnmf.run(i['X'], iteration=meta['iteration'], n_basis=meta['n_basis'], n_sources=meta['n_sources'],
+                             normalize=meta['normalize'], riccati=riccati, H=i['H0'], Z=i['Z0'], T=i['T0'], V=i['V0'])
+    tol = 1e-8
+    assert rel(out, o['output']) < tol
+    assert rel(st['H'], o['spatial']) < tol
+    assert rel(st['Z'], o['latent']) < tol and rel(st['T'], o['basis']) < tol and rel(st['V'], o['activation']) < tol
+    assert rel(loss, o['loss']) < tol
