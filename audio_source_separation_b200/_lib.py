@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libbssgpu.so')
 # enum bss_status
 OK, EINVAL, ECUDA, ESINGULAR, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 # enum bss_method
-GAUSS_ILRMA, T_ILRMA, AUX_LAPLACE_IVA, AUX_GAUSS_IVA, FAST_MNMF = 0, 1, 2, 3, 4
+GAUSS_ILRMA, T_ILRMA, AUX_LAPLACE_IVA, AUX_GAUSS_IVA, FAST_MNMF, IS_MNMF = 0, 1, 2, 3, 4, 5
 NMF_EUC, NMF_KL, NMF_IS, NMF_T, NMF_CAUCHY = 10, 11, 12, 13, 14
 # enum bss_spatial / bss_normalize / bss_nmf_algorithm
 SPATIAL_IP, SPATIAL_ISS, SPATIAL_IP2 = 0, 1, 2

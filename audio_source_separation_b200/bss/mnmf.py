@@ -1,4 +1,9 @@
-"""FastMNMF on the GPU with the reference's class surface (src/bss/mnmf.py).
+"""Multichannel NMF on the GPU with the reference's class surface (src/bss/mnmf.py).
+
+`MultichannelISNMF` (src/bss/mnmf.py:116-635, author='Sawada'): the four multiplicative updates of Sawada's MM algorithm
+(`update_basis_sawada`, `update_activation_sawada`, `update_latent_sawada`, `update_spatial_sawada` with the Riccati
+solve), `reconstruct_covariance`-based log-det loss and the multichannel Wiener filter, in fp64 on the device.  Ozerov's
+EM variant is "in progress" upstream and is not provided.
 
 `FastMultichannelISNMF` (src/bss/mnmf.py:637-946): same constructor arguments, `__call__`, `update_once`
 (`update_NMF`, `update_SCM`, `update_diagonalizer` and the three-step power normalisation), `separate`
@@ -6,8 +11,10 @@
 `compute_negative_loglikelihood`, callbacks and the public state attributes `basis`, `activation`,
 `diagonalizer`, `spatial_covariance`, `estimation`.  As in the reference, `_reset` re-creates `diagonalizer`
 and `spatial_covariance` unconditionally (:660-663, :688-689); only `basis` / `activation` can be preset
-through kwargs.  The Sawada MM / Ozerov EM `MultichannelISNMF` (:115-635) is not part of this package.
+through kwargs.
 """
+import warnings
+
 import numpy as np
 
 from .. import _lib
@@ -15,6 +22,12 @@ from .._model import DeviceModel, parse_normalize
 
 EPS = 1e-12
 THRESHOLD = 1e+12
+
+__authors__ = ['sawada', 'ozerov']
+
+__kwargs_sawada_mnmf___ = {
+    'reference_id': 0
+}
 
 
 class MultichannelNMFbase(DeviceModel):
@@ -71,6 +84,204 @@ class MultichannelNMFbase(DeviceModel):
 
     def compute_negative_loglikelihood(self):
         raise NotImplementedError("Implement 'compute_negative_loglikelihood' method.")
+
+
+class MultichannelISNMF(MultichannelNMFbase):
+    """
+    References:
+        Sawada's MNMF: "Multichannel Extensions of Non-Negative Matrix Factorization With Complex-Valued Data"
+    Drop-in for src/bss/mnmf.py:116-635 with author='Sawada'.  State attributes: `spatial` (n_bins, n_sources, n_channels,
+    n_channels), `latent` (n_sources, n_basis), `basis` (n_bins, n_basis), `activation` (n_basis, n_frames), `estimation`.
+    The reference's `covariance_input` (x x^H for every bin and frame, :222-223) is never materialised.
+    """
+
+    _STATE_IDS = {'basis': _lib.STATE_BASIS, 'activation': _lib.STATE_ACTIVATION, 'latent': _lib.STATE_LATENT,
+                  'spatial': _lib.STATE_SPATIAL, 'estimation': _lib.STATE_ESTIMATION}
+    _SNAPSHOT = ('basis', 'activation', 'latent', 'spatial')
+
+    def __init__(self, n_basis=10, n_sources=None, normalize=True, callbacks=None, reference_id=0, author='Sawada',
+                 recordable_loss=True, eps=EPS, **kwargs):
+        """
+        Args:
+            n_basis
+            n_sources
+            normalize
+            callbacks <callable> or <list<callable>>: Callback function. Default: None
+            reference_id <int>
+            author <str>: 'Sawada' ('Ozerov' is in progress upstream and not available here)
+            eps <float>: Machine epsilon
+        """
+        super().__init__(n_basis=n_basis, n_sources=n_sources, callbacks=callbacks, recordable_loss=recordable_loss, eps=eps)
+
+        self.normalize = normalize
+
+        assert author.lower() in __authors__, "Choose from {}".format(__authors__)
+
+        self.author = author
+
+        if author.lower() == 'sawada':
+            if set(kwargs) - set(__kwargs_sawada_mnmf___) != set():
+                raise ValueError("Invalid keywords.")
+            for key in __kwargs_sawada_mnmf___.keys():
+                setattr(self, key, __kwargs_sawada_mnmf___[key])
+            for key in kwargs.keys():
+                setattr(self, key, kwargs[key])
+            # the reference overwrites the constructor's reference_id with the keyword default (:144-147)
+        else:
+            warnings.warn("in progress", UserWarning)
+
+    # -- device plumbing -----------------------------------------------------------------------------
+    def _state_shape(self, name):
+        N, C, F, T, K = self.n_sources, self.n_channels, self.n_bins, self.n_frames, self.n_basis
+        return {'basis': (F, K), 'activation': (K, T), 'latent': (N, K), 'spatial': (F, N, C, C), 'estimation': (N, F, T)}[name]
+
+    def _state_dtype(self, name):
+        return np.complex128 if name in ('spatial', 'estimation') else np.float64
+
+    def _config(self):
+        return dict(method=_lib.IS_MNMF, normalize=_lib.NORMALIZE_POWER if self.normalize else _lib.NORMALIZE_NONE, n_batch=1,
+                    n_channels=self.n_channels, n_sources=self.n_sources, n_bins=self.n_bins, n_frames=self.n_frames,
+                    n_basis=self.n_basis, reference_id=self.reference_id, eps=float(self.eps))
+
+    def _prepare(self):
+        X = self.input
+        assert X is not None, "Specify data!"
+        if self.author.lower() != 'sawada':
+            raise NotImplementedError("Not support {}'s MNMF.".format(self.author))
+        cfg = self._config()
+        self._open_handle(tuple(sorted(cfg.items())), **cfg)
+        self._send_input(X)
+        self._push()
+
+    # -- reference surface -----------------------------------------------------------------------------
+    def _reset(self, **kwargs):
+        super()._reset(**kwargs)
+
+        author = self.author
+
+        if author.lower() == 'sawada':
+            self._reset_sawada()
+        elif author.lower() == 'ozerov':
+            raise NotImplementedError("Not support {}'s MNMF.".format(self.author))
+        else:
+            raise ValueError("Not support")
+
+        self._prepare()
+        self._on_device.update(('basis', 'activation', 'latent', 'spatial', 'estimation'))
+        self._device_changed('estimation')
+
+    def _reset_sawada(self):
+        """src/bss/mnmf.py:202-237: latent, basis, activation are drawn from the global NumPy state in that order."""
+        n_basis = self.n_basis
+        n_sources = self.n_sources
+        eps = self.eps
+
+        n_channels, n_bins, n_frames = self.input.shape
+
+        if not hasattr(self, 'latent'):
+            variance_latent = 1e-2
+            Z = np.random.rand(n_sources, n_basis) * variance_latent + 1 / n_sources
+            Zsum = Z.sum(axis=0)
+            Zsum[Zsum < eps] = eps
+            self.latent = Z / Zsum
+        else:
+            self.latent = np.array(self.latent, dtype=np.float64, copy=True)
+        if not hasattr(self, 'spatial'):
+            H = np.eye(n_channels)
+            self.spatial = np.tile(H, reps=(n_bins, n_sources, 1, 1))
+        else:
+            self.spatial = np.array(self.spatial, copy=True)
+        if not hasattr(self, 'basis'):
+            self.basis = np.random.rand(n_bins, n_basis)
+        else:
+            self.basis = np.array(self.basis, dtype=np.float64, copy=True)
+        if not hasattr(self, 'activation'):
+            self.activation = np.random.rand(n_basis, n_frames)
+        else:
+            self.activation = np.array(self.activation, dtype=np.float64, copy=True)
+
+    def __call__(self, input, iteration=100, **kwargs):
+        """
+        Args:
+            input (n_channels, n_bins, n_frames)
+        Returns:
+            output (n_sources, n_bins, n_frames)
+        """
+        self.input = input
+
+        self._reset(**kwargs)
+
+        if self.recordable_loss:
+            loss = self.compute_negative_loglikelihood()
+            self.loss.append(loss)
+
+        if self.callbacks is not None:
+            for callback in self.callbacks:
+                callback(self)
+
+        if self.callbacks is None:
+            # nothing observes the intermediate states: the loop (and its loss history) stays on the device
+            self._push()
+            if self.recordable_loss:
+                self.loss.extend(float(v) for v in self._handle.run_record(iteration)[:, 0])
+            else:
+                self._handle.run(iteration)
+            self._device_changed()
+        else:
+            for idx in range(iteration):
+                self.update_once()
+
+                if self.recordable_loss:
+                    loss = self.compute_negative_loglikelihood()
+                    self.loss.append(loss)
+
+                for callback in self.callbacks:
+                    callback(self)
+
+        output = self.separate(self.input)
+        self.estimation = output
+
+        return output
+
+    def __repr__(self):
+        s = "IS-MNMF("
+        s += "n_basis={n_basis}"
+        if hasattr(self, 'n_sources'):
+            s += ", n_sources={n_sources}"
+        if hasattr(self, 'n_channels'):
+            s += ", n_channels={n_channels}"
+        s += ", normalize={normalize}"
+        s += ", author={author}"
+        s += ")"
+
+        return s.format(**self.__dict__)
+
+    def update_once(self):
+        """update_basis_sawada, update_activation_sawada, update_latent_sawada, update_spatial_sawada (:311-315); the
+        estimate the reference recomputes here (:308-309) is produced when `estimation` is read."""
+        self._prepare()
+        self._handle.update_once()
+        self._device_changed()
+
+    def reconstruct_covariance(self):
+        """X_hat (n_bins, n_frames, n_channels, n_channels) of the current model (src/bss/mnmf.py:554-562); host-side
+        convenience for callbacks, the device never stores it."""
+        H, Z, T, V = self.spatial, self.latent, self.basis, self.activation
+        HZ = np.einsum('fnij,nk->fkij', H, Z)
+        return np.einsum('fkij,fk,kt->ftij', HZ, T, V)
+
+    def compute_negative_loglikelihood(self):
+        self._prepare()
+        return float(self._handle.loss()[0])
+
+    def separate(self, input):
+        """Multichannel Wiener filter with the current model, image at `reference_id`; `input` must be the mixture the
+        model holds (src/bss/mnmf.py:609-634 is only ever called that way)."""
+        if input is not self.input:
+            if self.input is None or np.shape(input) != np.shape(self.input) or not np.array_equal(input, self.input):
+                raise NotImplementedError("separate() is available for the model's own input")
+        self._prepare()
+        return self._handle.separate((self.n_sources, self.n_bins, self.n_frames), np.complex128, projection_back=False)
 
 
 class FastMultichannelISNMF(MultichannelNMFbase):
@@ -244,3 +455,4 @@ class FastMultichannelISNMF(MultichannelNMFbase):
 
 
 FastMNMF = FastMultichannelISNMF
+MNMF = MultichannelISNMF

@@ -37,6 +37,12 @@ int validate(const bss_config* c, std::string* why) {
         return BSS_OK;
     }
     if (c->n_channels < 2 || c->n_channels > 8) return bad("n_channels must be between 2 and 8");
+    if (c->method == BSS_IS_MNMF) {
+        if (c->n_channels > 4) return bad("IS-MNMF supports 2 to 4 channels");
+        if (c->n_sources < 1 || c->n_sources > 8) return bad("n_sources must be between 1 and 8");
+        if (c->reference_id < 0 || c->reference_id >= c->n_channels) return bad("reference_id out of range");
+        return BSS_OK;
+    }
     if (c->method == BSS_FAST_MNMF) {
         if (c->n_sources < 1 || c->n_sources > 8) return bad("n_sources must be between 1 and 8");
     } else {
@@ -149,7 +155,16 @@ int bss_create(const bss_config* cfg, bss_handle** out) {
     CREATE_CUDA(cudaEventCreate(&h->ev0));
     CREATE_CUDA(cudaEventCreate(&h->ev1));
     int rc = dev_alloc(h, &h->flags, 4);
-    if (rc == BSS_OK) rc = is_nmf(cfg->method) ? nmf_allocate(h) : (cfg->method == BSS_FAST_MNMF ? mnmf_allocate(h) : bss_allocate(h));
+    if (rc == BSS_OK) {
+        if (is_nmf(cfg->method))
+            rc = nmf_allocate(h);
+        else if (cfg->method == BSS_FAST_MNMF)
+            rc = mnmf_allocate(h);
+        else if (cfg->method == BSS_IS_MNMF)
+            rc = smnmf_allocate(h);
+        else
+            rc = bss_allocate(h);
+    }
     if (rc != BSS_OK) return fail(rc);
     CREATE_CUDA(cudaStreamSynchronize(h->stream));
 #undef CREATE_CUDA
@@ -164,7 +179,8 @@ void bss_destroy(bss_handle* h) {
     void* bufs[] = {h->X,   h->Y,    h->W,     h->Wf,    h->basis, h->basis2, h->act,     h->latent, h->U,      h->Cx,
                     h->gate, h->flags, h->pw,   h->scale, h->wfr,   h->wraw,   h->order,   h->logdet, h->aux,    h->G2x,
                     h->part, h->iw,   h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
-                    h->nz,   h->nt,   h->nv,    h->npart, h->loss_hist, h->G2, h->beff, h->aeff, h->praw};
+                    h->nz,   h->nt,   h->nv,    h->npart, h->loss_hist, h->G2, h->beff, h->aeff, h->praw,
+                    h->sH,   h->sZ,   h->sT,    h->sV,    h->sStat, h->sPart, h->sAcc};
     for (void* p : bufs)
         if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -239,7 +255,7 @@ static int finish_input(bss_handle* h) {
     ca.wmode = WM_UNIT;
     ca.n_sel = 1;
     ca.wsel[0] = 0;
-    BSS_TRY(launch_covariance(h, ca));
+    if (h->cfg.method != BSS_IS_MNMF) BSS_TRY(launch_covariance(h, ca));
     h->has_input = true;
     h->y_valid = false;
     // ISS carries estimates instead of a filter: (re)derive them when the filter came first
@@ -254,6 +270,7 @@ int bss_reset_spatial(bss_handle* h) {
     if (is_nmf(h->cfg.method)) return BSS_OK;
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->cfg.method == BSS_FAST_MNMF) return mnmf_reset(h);
+    if (h->cfg.method == BSS_IS_MNMF) return smnmf_reset(h);
     return bss_reset_filter(h);
 }
 
@@ -276,6 +293,7 @@ int bss_update_once(bss_handle* h) {
         case BSS_AUX_LAPLACE_IVA:
         case BSS_AUX_GAUSS_IVA: return auxiva_update_once(h);
         case BSS_FAST_MNMF: return mnmf_update_once(h);
+        case BSS_IS_MNMF: return smnmf_update_once(h);
     }
     return bss_fail(h, BSS_EINVAL, "unknown method");
 }
@@ -348,6 +366,7 @@ int bss_run(bss_handle* h, int n_iter) {
 static int loss_device(bss_handle* h) {
     if (is_nmf(h->cfg.method)) return nmf_loss(h);
     if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    if (h->cfg.method == BSS_IS_MNMF) return smnmf_loss(h);
     return h->cfg.method == BSS_FAST_MNMF ? mnmf_loss(h) : bss_loss_device(h);
 }
 
@@ -387,7 +406,7 @@ int bss_loss(bss_handle* h, double* loss) {
         rc = nmf_loss(h);
     else {
         if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
-        rc = h->cfg.method == BSS_FAST_MNMF ? mnmf_loss(h) : bss_loss_device(h);
+        rc = loss_device(h);
     }
     if (rc != BSS_OK) return rc;
     // results sit at lossbuf[B*F .. B*F+B)
@@ -402,6 +421,7 @@ int bss_separate_device(bss_handle* h, void* y_device, int apply_projection_back
     if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->cfg.method == BSS_FAST_MNMF) return mnmf_separate(h, (cf*)y_device);
+    if (h->cfg.method == BSS_IS_MNMF) return smnmf_separate(h, (cf*)y_device);
     return bss_separate_to(h, (cf*)y_device, apply_projection_back);
 }
 
@@ -439,7 +459,8 @@ int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int h
 
 int bss_compute_demix_filter(bss_handle* h) {
     if (!h) return BSS_EINVAL;
-    if (is_nmf(h->cfg.method) || h->cfg.method == BSS_FAST_MNMF) return bss_fail(h, BSS_EINVAL, "no demixing filter");
+    if (is_nmf(h->cfg.method) || h->cfg.method == BSS_FAST_MNMF || h->cfg.method == BSS_IS_MNMF)
+        return bss_fail(h, BSS_EINVAL, "no demixing filter");
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
     return bss_filter_from_estimates(h);
 }
@@ -473,7 +494,7 @@ int bss_device_buffer(bss_handle* h, int which, void** dptr, size_t* bytes) {
 
 int bss_time_covariance(bss_handle* h, int repeat, float* mean_ms) {
     if (!h || !mean_ms || repeat < 1) return BSS_EINVAL;
-    if (is_nmf(h->cfg.method) || !h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    if (is_nmf(h->cfg.method) || h->cfg.method == BSS_IS_MNMF || !h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
     BSS_TRY(bss_covariance_only(h));   // warm-up
     BSS_CUDA(h, cudaEventRecord(h->ev0, h->stream));

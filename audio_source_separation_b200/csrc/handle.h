@@ -82,6 +82,14 @@ struct bss_handle {
     double* nv = nullptr;
     double* npart = nullptr;       // partial sums of the activation update
     size_t npart_elems = 0;
+    // Sawada IS-MNMF (fp64 throughout)
+    double* sH = nullptr;          // [B][F][N][C*C] packed Hermitian spatial covariances
+    double* sZ = nullptr;          // [B][N][K] latent
+    double* sT = nullptr;          // [B][F][K] basis
+    double* sV = nullptr;          // [B][K][T] activation
+    double* sStat = nullptr;       // [2][B][N][F][T] tr(Xh^-1 X Xh^-1 H_n), tr(Xh^-1 H_n)
+    double* sPart = nullptr;       // partial sums of the factor updates
+    double* sAcc = nullptr;        // [B][F][N][2][C*C] packed: sum_t lambda Xh^-1, sum_t lambda q q^H
     // loss history of bss_run_record: [n_iter][B]
     double* loss_hist = nullptr;
     size_t loss_hist_elems = 0;
@@ -292,4 +300,11 @@ int launch_covariance_mma(bss_handle* h, const cf* X, const float* iw_tiled, dou
 int launch_mnmf_loss_terms(bss_handle* h);
 int launch_mnmf_separate(bss_handle* h, cf* out);
 int launch_mnmf_normalize(bss_handle* h);
+// Sawada IS-MNMF (kernels_smnmf.cu)
+void smnmf_act_plan(const bss_handle* h, int* bins, int* chunks);
+int launch_smnmf_stats(bss_handle* h);
+int launch_smnmf_factor(bss_handle* h, int which);
+int launch_smnmf_spatial(bss_handle* h, int normalize);
+int launch_smnmf_loss_terms(bss_handle* h, double* terms);
+int launch_smnmf_separate(bss_handle* h, cf* out);
 int launch_sum_frames(bss_handle* h, const float* raw, int B, int N, int T, int Tp, int kind, double coef, double eps, double* out);

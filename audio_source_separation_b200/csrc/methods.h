@@ -25,6 +25,15 @@ int mnmf_update_once(bss_handle* h);
 int mnmf_loss(bss_handle* h);
 int mnmf_separate(bss_handle* h, cf* out);
 
+// Sawada IS-MNMF: methods_smnmf.cu
+int smnmf_allocate(bss_handle* h);
+int smnmf_reset(bss_handle* h);
+int smnmf_update_once(bss_handle* h);
+int smnmf_loss(bss_handle* h);
+int smnmf_separate(bss_handle* h, cf* out);
+int smnmf_set_state(bss_handle* h, int which, const void* src, int dtype);
+int smnmf_get_state(bss_handle* h, int which, void* dst, int dtype);
+
 // single-channel NMF: methods_nmf.cu
 int nmf_allocate(bss_handle* h);
 int nmf_update_once(bss_handle* h);

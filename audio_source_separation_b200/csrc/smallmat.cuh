@@ -304,3 +304,93 @@ SM_HD int ip_row(Mat<C>& W, const Mat<C>& U, int n, double threshold, bool use_g
     }
     return ok ? 1 : 0;
 }
+
+// ------------------------------------------------------------------------------ Hermitian eigen / Riccati
+// Two-sided (classical cyclic) Jacobi for a Hermitian matrix: A = V diag(w) V^H.  Only the Hermitian part of the
+// input is used.  A pair (p,q) is first made real by the phase of a_pq, then rotated by the real Jacobi angle.
+template <int C>
+SM_HD void herm_eig(const Mat<C>& Ain, Mat<C>& V, double* w) {
+    Mat<C> A;
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j) {
+            const cd a = Ain.a[i][j], b = cd_conj(Ain.a[j][i]);
+            A.a[i][j] = cd_make(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+            V.a[i][j] = cd_make(i == j ? 1.0 : 0.0, 0.0);
+        }
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < C; ++i) {
+            diag += A.a[i][i].x * A.a[i][i].x;
+            for (int j = 0; j < i; ++j) off += cd_abs2(A.a[i][j]);
+        }
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < C - 1; ++p)
+            for (int q = p + 1; q < C; ++q) {
+                const cd apq = A.a[p][q];
+                const double g = cd_abs(apq);
+                if (g == 0.0) continue;
+                const cd ph = cd_make(apq.x / g, apq.y / g);                 // e^{i phi}
+                const double tau = (A.a[q][q].x - A.a[p][p].x) / (2.0 * g);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                // columns: (a_ip, a_iq) <- (c a_ip - s e^{-i phi} a_iq, s a_ip + c e^{-i phi} a_iq); same for V
+                for (int i = 0; i < C; ++i) {
+                    cd xp = A.a[i][p], xq = A.a[i][q] * cd_conj(ph);
+                    A.a[i][p] = cd_make(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                    A.a[i][q] = cd_make(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+                    xp = V.a[i][p];
+                    xq = V.a[i][q] * cd_conj(ph);
+                    V.a[i][p] = cd_make(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                    V.a[i][q] = cd_make(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+                }
+                // rows: the conjugate transpose of the same rotation from the left
+                for (int j = 0; j < C; ++j) {
+                    const cd xp = A.a[p][j], xq = A.a[q][j] * ph;
+                    A.a[p][j] = cd_make(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                    A.a[q][j] = cd_make(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+                }
+                A.a[p][q] = cd_make(0.0, 0.0);
+                A.a[q][p] = cd_make(0.0, 0.0);
+                A.a[p][p].y = 0.0;
+                A.a[q][q].y = 0.0;
+            }
+    }
+    for (int i = 0; i < C; ++i) w[i] = A.a[i][i].x;
+}
+
+// R = V diag(f) V^H
+template <int C>
+SM_HD void herm_compose(const Mat<C>& V, const double* f, Mat<C>& R) {
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j) {
+            cd s = cd_make(0.0, 0.0);
+            for (int k = 0; k < C; ++k) cd_fma(s, f[k] * V.a[i][k], cd_conj(V.a[j][k]));
+            R.a[i][j] = s;
+        }
+}
+
+// The positive semi-definite solution of H A H = B for Hermitian positive (semi-)definite A, B:
+// H = A^-1/2 (A^1/2 B A^1/2)^1/2 A^-1/2, Hermitian part.  Replaces solve_Riccati (src/algorithm/linalg.py:7-30), which
+// takes the same solution from the stable invariant subspace of the 2C x 2C matrix [[0,-A],[-B,0]].
+template <int C>
+SM_HD void riccati_hermitian(const Mat<C>& A, const Mat<C>& B, Mat<C>& H) {
+    Mat<C> V, S, Si, M, R;
+    double w[C], f[C];
+    herm_eig(A, V, w);
+    for (int i = 0; i < C; ++i) f[i] = sqrt(fmax(w[i], 0.0));
+    herm_compose(V, f, S);
+    for (int i = 0; i < C; ++i) f[i] = 1.0 / f[i];
+    herm_compose(V, f, Si);
+    mat_mul(S, B, R);
+    mat_mul(R, S, M);
+    herm_eig(M, V, w);
+    for (int i = 0; i < C; ++i) f[i] = sqrt(fmax(w[i], 0.0));
+    herm_compose(V, f, M);
+    mat_mul(Si, M, R);
+    mat_mul(R, Si, M);
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j) {
+            const cd a = M.a[i][j], b = cd_conj(M.a[j][i]);
+            H.a[i][j] = cd_make(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+        }
+}

@@ -77,6 +77,7 @@ int bss_set_state(bss_handle* h, int which, const void* src, int dtype) {
         }
         return bss_fail(h, BSS_EINVAL, "state cannot be set");
     }
+    if (h->cfg.method == BSS_IS_MNMF) return smnmf_set_state(h, which, src, dtype);
     switch (which) {
         case BSS_STATE_DEMIX_FILTER:
         case BSS_STATE_DIAGONALIZER: {
@@ -125,6 +126,7 @@ int bss_get_state(bss_handle* h, int which, void* dst, int dtype) {
         }
         return bss_fail(h, BSS_EINVAL, "unknown state");
     }
+    if (h->cfg.method == BSS_IS_MNMF) return smnmf_get_state(h, which, dst, dtype);
     switch (which) {
         case BSS_STATE_DEMIX_FILTER:
         case BSS_STATE_DIAGONALIZER: {

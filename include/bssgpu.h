@@ -47,6 +47,7 @@ enum bss_method {
     BSS_AUX_LAPLACE_IVA = 2,  /* src/bss/iva.py:388    AuxLaplaceIVA         */
     BSS_AUX_GAUSS_IVA = 3,    /* src/bss/iva.py:621    AuxGaussIVA           */
     BSS_FAST_MNMF = 4,        /* src/bss/mnmf.py:637   FastMultichannelISNMF */
+    BSS_IS_MNMF = 5,          /* src/bss/mnmf.py:116   MultichannelISNMF(author='Sawada'); `normalize` != 0 is normalize=True */
     BSS_NMF_EUC = 10,         /* src/algorithm/nmf.py:150 EUCNMF             */
     BSS_NMF_KL = 11,          /* src/algorithm/nmf.py:209 KLNMF              */
     BSS_NMF_IS = 12,          /* src/algorithm/nmf.py:268 ISNMF              */
@@ -83,6 +84,7 @@ enum bss_dtype { BSS_F32 = 0, BSS_F64 = 1, BSS_C64 = 2, BSS_C128 = 3, BSS_I32 = 
  *   LATENT         (N,K)   real      model.latent       (partitioning only)
  *   DIAGONALIZER   (F,M,M) complex   FastMNMF model.diagonalizer
  *   SPATIAL        (N,F,M) real      FastMNMF model.spatial_covariance
+ *                  (F,N,C,C) complex IS-MNMF model.spatial (Hermitian; basis (F,K), activation (K,T), latent (N,K))
  *   TARGET         (F,T)   real      NMF target
  *   COVARIANCE     (N,F,C,C) complex weighted covariances of the last spatial update (read only)
  *   GATE           (N,F)   int32     condition-number gate decisions of the last IP update (read only)

@@ -63,6 +63,23 @@ static void det(const double* A, double* out) {
     out[1] = d.y;
 }
 
+template <int C>
+static void riccati(const double* A, const double* B, double* out) {
+    Mat<C> Am, Bm, H;
+    load<C>(A, Am);
+    load<C>(B, Bm);
+    riccati_hermitian<C>(Am, Bm, H);
+    store<C>(out, H);
+}
+
+template <int C>
+static void eigh(const double* A, double* vecs, double* vals) {
+    Mat<C> Am, V;
+    load<C>(A, Am);
+    herm_eig<C>(Am, V, vals);
+    store<C>(vecs, V);
+}
+
 #define DISPATCH(C, EXPR)              \
     switch (C) {                       \
         case 2: { constexpr int K = 2; EXPR; } break; \
@@ -92,6 +109,14 @@ int hm_inverse(int C, const double* A, double* out) {
 }
 int hm_det(int C, const double* A, double* out) {
     DISPATCH(C, det<K>(A, out))
+    return 0;
+}
+int hm_riccati(int C, const double* A, const double* B, double* out) {
+    DISPATCH(C, riccati<K>(A, B, out))
+    return 0;
+}
+int hm_eigh(int C, const double* A, double* vecs, double* vals) {
+    DISPATCH(C, eigh<K>(A, vecs, vals))
     return 0;
 }
 }

@@ -25,6 +25,8 @@ def hm():
     lib.hm_cond2.argtypes = [i, vp, vp]
     lib.hm_inverse.argtypes = [i, vp, vp]
     lib.hm_det.argtypes = [i, vp, vp]
+    lib.hm_riccati.argtypes = [i, vp, vp, vp]
+    lib.hm_eigh.argtypes = [i, vp, vp, vp]
     return lib
 
 
@@ -126,3 +128,30 @@ def test_ip_gate_decisions_near_threshold(hm):
     ok = gate_o[0]
     assert rel(Wg[ok, 0], Wo[ok, 0]) < 1e-3   # cond up to 1e12: eps * cond
     assert np.array_equal(Wg[~ok, 0], W0[~ok, 0])
+
+
+@pytest.mark.parametrize('C', [2, 3, 4])
+def test_hermitian_eig_and_riccati(hm, C):
+    """Jacobi eigen-decomposition and the closed-form Riccati solution the IS-MNMF spatial update runs, against
+    LAPACK `eigh` and the oracle's restatement of solve_Riccati (src/algorithm/linalg.py:7-30)."""
+    from oracle import mnmf
+    rng = np.random.default_rng(10 + C)
+    for trial in range(20):
+        G = _rand_c(rng, C, C)
+        A = np.ascontiguousarray(G @ G.conj().T + 0.1 * np.eye(C))
+        G = _rand_c(rng, C, C)
+        B = np.ascontiguousarray(G @ G.conj().T * 10.0 ** rng.integers(-3, 3))
+        vecs, vals = np.empty_like(A), np.empty(C)
+        hm.hm_eigh(C, _p(A), _p(vecs), _p(vals))
+        assert rel(np.sort(vals), np.linalg.eigvalsh(A)) < 1e-12
+        assert rel((vecs * vals) @ vecs.conj().T, A) < 1e-12
+        H = np.empty_like(A)
+        hm.hm_riccati(C, _p(A), _p(B), _p(H))
+        assert rel(H @ A @ H, B) < 1e-10
+        assert rel(H, mnmf.solve_riccati(A[None, None], B[None, None])[0, 0]) < 1e-9
+    # identity / diagonal inputs (the very first spatial update starts from H = I)
+    A = np.ascontiguousarray(np.diag(rng.random(C) + 0.5).astype(np.complex128))
+    B = np.ascontiguousarray(np.diag(rng.random(C) + 0.5).astype(np.complex128))
+    H = np.empty_like(A)
+    hm.hm_riccati(C, _p(A), _p(B), _p(H))
+    assert rel(H, np.diag(np.sqrt(np.diag(B).real / np.diag(A).real))) < 1e-13

@@ -4,7 +4,7 @@ Gauss-ILRMA, cfg4 FastMNMF) on one GPU, device time per update_once (CUDA events
 without host synchronisation) next to the oracle port on the host for a few iterations.  One JSON line per config.
 bench.py remains the headline measurement; this script only fills the table in profiles/.
 
-    python tools/bench_configs.py [--skip-cpu] [--configs cfg1,cfg2,cfg3,cfg4]
+    python tools/bench_configs.py [--skip-cpu] [--configs cfg1,cfg2,cfg3,cfg4,mnmf]
 """
 import argparse
 import json
@@ -152,12 +152,42 @@ def cfg4(skip_cpu):
     return out
 
 
+def mnmf(skip_cpu):
+    """Sawada IS-MNMF at the shape of the reference's MNMF notebook input: 2 channels,
+    2049 bins, 256 frames, 2 sources, n_basis = 10 (the constructor default)."""
+    from audio_source_separation_b200.bss.mnmf import MultichannelISNMF
+    from oracle import mnmf as o_mnmf, synth
+    C, N, F, T, K = 2, 2, 2049, 256, 10
+    X = synth.mix2(C, F, T, seed=0)
+    np.random.seed(111)
+    model = MultichannelISNMF(n_basis=K, n_sources=N, recordable_loss=False)
+    model.input = X
+    model._reset()
+    Z0, T0, V0 = model.latent.copy(), model.basis.copy(), model.activation.copy()
+    ms = device_loop_ms(model._handle, 50, warmup=3)
+    out = {"config": "IS-MNMF (Sawada) 2ch 2049x256 N=2 K=10", "gpu_ms_per_iter": ms, "gpu_it_per_s": 1e3 / ms}
+    out["loss_finite"] = bool(np.isfinite(model.compute_negative_loglikelihood()))
+    C4 = MultichannelISNMF(n_basis=K, n_sources=4, recordable_loss=False)
+    C4.input = synth.mix2(4, F, 512, seed=0)
+    C4._reset()
+    out["gpu_ms_per_iter_4ch_512frames_N4"] = device_loop_ms(C4._handle, 20, warmup=3)
+    if not skip_cpu:
+        Fs = 128
+        st = o_mnmf.init_state(X[:, :Fs], K, N, Z=Z0, T=T0[:Fs], V=V0)
+
+        def step():
+            o_mnmf.update_once(st)
+        c = cpu_ms(step, 2) * (F / Fs)
+        out.update(cpu_ms_per_iter=c, cpu_note="oracle on a 128-bin slice x {:.1f}".format(F / Fs), speedup=c / ms)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--configs', default='cfg1,cfg2,cfg3,cfg4')
     args = ap.parse_args()
-    fns = {'cfg1': cfg1, 'cfg2': cfg2, 'cfg3': cfg3, 'cfg4': cfg4}
+    fns = {'cfg1': cfg1, 'cfg2': cfg2, 'cfg3': cfg3, 'cfg4': cfg4, 'mnmf': mnmf}
     for name in args.configs.split(','):
         print(json.dumps(fns[name](args.skip_cpu)), flush=True)
 
