@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libbssgpu.so')
 # enum bss_status
 OK, EINVAL, ECUDA, ESINGULAR, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 # enum bss_method
-GAUSS_ILRMA, T_ILRMA, AUX_LAPLACE_IVA, AUX_GAUSS_IVA, FAST_MNMF, IS_MNMF = 0, 1, 2, 3, 4, 5
+GAUSS_ILRMA, T_ILRMA, AUX_LAPLACE_IVA, AUX_GAUSS_IVA, FAST_MNMF, IS_MNMF, GAUSS_IDLMA = 0, 1, 2, 3, 4, 5, 6
 NMF_EUC, NMF_KL, NMF_IS, NMF_T, NMF_CAUCHY = 10, 11, 12, 13, 14
 # enum bss_spatial / bss_normalize / bss_nmf_algorithm
 SPATIAL_IP, SPATIAL_ISS, SPATIAL_IP2 = 0, 1, 2
@@ -24,7 +24,7 @@ ALG_MM, ALG_ME, ALG_NAIVE, ALG_MM_FAST = 0, 1, 2, 3
 F32, F64, C64, C128, I32 = 0, 1, 2, 3, 4
 # enum bss_state
 (STATE_DEMIX_FILTER, STATE_ESTIMATION, STATE_BASIS, STATE_ACTIVATION, STATE_LATENT, STATE_DIAGONALIZER,
- STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE) = range(10)
+ STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE, STATE_VARIANCE) = range(11)
 
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64,
            np.dtype(np.complex128): C128, np.dtype(np.int32): I32}
@@ -60,6 +60,7 @@ SIGNATURES = {
     'bss_reset_spatial': (_i, [_vp]),
     'bss_set_update_pair': (_i, [_vp, _i, _i]),
     'bss_update_once': (_i, [_vp]),
+    'bss_normalize': (_i, [_vp]),
     'bss_run': (_i, [_vp, _i]),
     'bss_run_record': (_i, [_vp, _i, ctypes.POINTER(_d)]),
     'bss_loss': (_i, [_vp, ctypes.POINTER(_d)]),
@@ -209,6 +210,9 @@ class Handle:
 
     def update_once(self):
         self._check(self._lib.bss_update_once(self._h))
+
+    def normalize(self):
+        self._check(self._lib.bss_normalize(self._h))
 
     def run(self, n_iter):
         self._check(self._lib.bss_run(self._h, int(n_iter)))

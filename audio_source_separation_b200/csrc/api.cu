@@ -59,6 +59,10 @@ int validate(const bss_config* c, std::string* why) {
         case BSS_AUX_LAPLACE_IVA:
         case BSS_AUX_GAUSS_IVA:
         case BSS_FAST_MNMF: break;
+        case BSS_GAUSS_IDLMA:
+            if (c->spatial != BSS_SPATIAL_IP) return bad("GaussIDLMA updates the spatial model by IP only");
+            if (!(c->domain >= 1.0 && c->domain <= 2.0)) return bad("1 <= `domain` <= 2 is not satisfied.");
+            break;
         default: return bad("unknown method");
     }
     return BSS_OK;
@@ -292,10 +296,20 @@ int bss_update_once(bss_handle* h) {
         case BSS_T_ILRMA: return tilrma_update_once(h);
         case BSS_AUX_LAPLACE_IVA:
         case BSS_AUX_GAUSS_IVA: return auxiva_update_once(h);
+        case BSS_GAUSS_IDLMA: return idlma_update_once(h);
         case BSS_FAST_MNMF: return mnmf_update_once(h);
         case BSS_IS_MNMF: return smnmf_update_once(h);
     }
     return bss_fail(h, BSS_EINVAL, "unknown method");
+}
+
+int bss_normalize(bss_handle* h) {
+    if (!h) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.method != BSS_GAUSS_IDLMA)
+        return bss_fail(h, BSS_EUNSUPPORTED, "normalisation is part of update_once for this method");
+    if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    return idlma_normalize(h);
 }
 
 // n eager iterations (advances the IP2 pair schedule like the reference's __call__, src/bss/ilrma.py:635-646)

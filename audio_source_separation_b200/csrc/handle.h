@@ -31,6 +31,7 @@ struct bss_handle {
 
     bool has_input = false;
     bool has_filter = false;      // W holds a valid demixing filter (false for ISS between updates)
+    bool has_variance = false;    // GaussIDLMA: BSS_STATE_VARIANCE has been set
     bool y_valid = false;         // Y buffer holds separate(X, W) / the ISS state
     int pair_m = -1, pair_n = -1; // IP2 pair
     bool pair_started = false;
@@ -263,6 +264,8 @@ int launch_frame_weights(bss_handle* h, const cf* src, const cf* Wf, int from_y,
 int launch_t_weights(bss_handle* h, const cf* X, const cf* Wf, const float* basis, const float* act, float* iw, int B, int C,
                      int F, int K, int Tp, float nu, float eps);
 int launch_import_weights(bss_handle* h, const double* r_dev, float* iw, int N, int F, int T, int Tp);
+int launch_import_variance(bss_handle* h, const double* r_dev, float* iw, int B, int N, int F, int T, int Tp, double eps);
+int launch_idlma_loss(bss_handle* h, const cf* X, const cf* Wf, const float* iw, double* terms, int B, int C, int F, int T, int Tp);
 int launch_iss(bss_handle* h, cf* Y, int mode, const float* basis, const float* act, const float* wfr, double* pw, int B, int N,
                int F, int T, int Tp, int K, float expo, float eps);
 int launch_cross_cov(bss_handle* h, const cf* Y, const cf* X, double2* G, long long n_bins, int C, int T, int Tp);

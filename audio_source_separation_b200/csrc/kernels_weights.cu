@@ -180,6 +180,56 @@ __global__ void __launch_bounds__(256) import_weights_kernel(const double* r, fl
     iw[idx] = t < T ? (float)(1.0 / r[((size_t)n * F + f) * T + t]) : 0.f;
 }
 
+// GaussIDLMA: staged host (B,N,F,T) float64 variances R -> iw [B][F][N][Tp] = 1 / max(R, eps)
+// (the floor of src/sss/idlma.py:190; the pad frame gets weight 0)
+__global__ void __launch_bounds__(256) import_variance_kernel(const double* r, float* iw, int B, int N, int F, int T, int Tp,
+                                                              double eps) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * F * N * Tp) return;
+    const int t = (int)(idx % Tp);
+    long long q = idx / Tp;
+    const int n = (int)(q % N);
+    q /= N;
+    const int f = (int)(q % F);
+    const int b = (int)(q / F);
+    float v = 0.f;
+    if (t < T) {
+        double x = r[(((size_t)b * N + n) * F + f) * T + t];
+        x = x < eps ? eps : x;
+        v = (float)(1.0 / x);
+    }
+    iw[idx] = v;
+}
+
+// GaussIDLMA loss terms (src/sss/idlma.py:246-258): terms[bf] = sum_n sum_{t<T} (|y_n|^2 / R + log R), y = W_f x,
+// one warp per bin; R is held as its inverse
+__global__ void __launch_bounds__(128) idlma_loss_kernel(const cf* X, const cf* Wf, const float* iw, double* terms,
+                                                         long long n_items, int C, int T, int Tp) {
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int lane = threadIdx.x & 31;
+    const cf* x = X + (size_t)item * C * Tp;
+    const cf* w = Wf + (size_t)item * C * C;
+    const float* r = iw + (size_t)item * C * Tp;
+    double s = 0.0;
+    for (int t = lane; t < T; t += 32) {
+        cf xv[8];
+        for (int c = 0; c < C; ++c) xv[c] = x[tile_off(C, Tp, c, t)];
+        for (int n = 0; n < C; ++n) {
+            float yr = 0.f, yi = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const cf wv = __ldg(w + n * C + c);
+                yr = fmaf(wv.x, xv[c].x, fmaf(-wv.y, xv[c].y, yr));
+                yi = fmaf(wv.x, xv[c].y, fmaf(wv.y, xv[c].x, yi));
+            }
+            const float inv = r[(size_t)n * Tp + t];
+            s += (double)((yr * yr + yi * yi) * inv) - log((double)inv);
+        }
+    }
+    s = warp_sum(s);
+    if (lane == 0) terms[item] = s;
+}
+
 }  // namespace
 
 #define BSS_DISPATCH_C(Cval, CALL)                                                     \
@@ -273,6 +323,22 @@ int launch_t_weights(bss_handle* h, const cf* X, const cf* Wf, const float* basi
 int launch_import_weights(bss_handle* h, const double* r_dev, float* iw, int N, int F, int T, int Tp) {
     const long long n = (long long)F * N * Tp;
     import_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(r_dev, iw, N, F, T, Tp);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_import_variance(bss_handle* h, const double* r_dev, float* iw, int B, int N, int F, int T, int Tp, double eps) {
+    const long long n = (long long)B * F * N * Tp;
+    import_variance_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(r_dev, iw, B, N, F, T, Tp, eps);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_idlma_loss(bss_handle* h, const cf* X, const cf* Wf, const float* iw, double* terms, int B, int C, int F, int T, int Tp) {
+    const long long n_items = (long long)B * F;
+    idlma_loss_kernel<<<(unsigned)cdiv(n_items, 4), 128, 0, h->stream>>>(X, Wf, iw, terms, n_items, C, T, Tp);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;

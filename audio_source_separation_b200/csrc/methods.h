@@ -8,6 +8,9 @@ int bss_reset_filter(bss_handle* h);
 int ilrma_update_once(bss_handle* h);
 int tilrma_update_once(bss_handle* h);
 int auxiva_update_once(bss_handle* h);
+int idlma_update_once(bss_handle* h);                     // GaussIDLMA.update_space_model
+int idlma_normalize(bss_handle* h);                       // normalisation tail of GaussIDLMA.update_once
+int idlma_set_variance(bss_handle* h, const double* r);   // host (B,N,F,T) -> iw = 1 / max(r, eps)
 int bss_loss_device(bss_handle* h);                       // result in lossbuf[B*F .. B*F+B)
 int bss_separate_to(bss_handle* h, cf* out, int apply_pb); // out: device (B,N,F,T) complex64
 int bss_filter_from_estimates(bss_handle* h);

@@ -169,6 +169,7 @@ int bss_allocate(bss_handle* h) {
     } else {
         BSS_TRY(dalloc(h, &h->wfr, B * N * Tp));
         BSS_TRY(dalloc(h, &h->wraw, B * N * Tp));
+        if (h->cfg.method == BSS_GAUSS_IDLMA && !h->iw) BSS_TRY(dalloc(h, &h->iw, B * F * N * Tp));
     }
     if (is_iss(h)) {
         BSS_TRY(dalloc(h, &h->Y, B * F * N * Tp));
@@ -306,6 +307,37 @@ int auxiva_update_once(bss_handle* h) {
     return BSS_OK;
 }
 
+// GaussIDLMA (src/sss/idlma.py:142-210): the source variances are whatever the caller's DNN produced
+// (BSS_STATE_VARIANCE); the handle owns the spatial half: U[n,f] = mean_t x x^H / R[n,f,t], the gated IP sweep,
+// and (bss_normalize) the projection-back normalisation (W <- diag(scale) W, what :155-158 computes by least squares)
+int idlma_set_variance(bss_handle* h, const double* r) {
+    const size_t n = (size_t)h->B * h->N * h->F * h->T;
+    BSS_TRY(ensure_staging(h, n * sizeof(double)));
+    BSS_CUDA(h, cudaMemcpyAsync(h->staging, r, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    BSS_TRY(launch_import_variance(h, (const double*)h->staging, h->iw, h->B, h->N, h->F, h->T, h->Tp, h->cfg.eps));
+    BSS_CUDA(h, cudaStreamSynchronize(h->stream));   // the host buffer is borrowed for this call only
+    h->has_variance = true;
+    return BSS_OK;
+}
+
+int idlma_update_once(bss_handle* h) {
+    if (!h->has_variance) return bss_fail(h, BSS_ESTATE, "GaussIDLMA: set the source variances (dnn_output) first");
+    if (!h->has_filter) return bss_fail(h, BSS_ESTATE, "GaussIDLMA: no demixing filter");
+    CovArgs c = cov_args(h);
+    c.wmode = WM_EXPLICIT;
+    BSS_TRY(launch_covariance(h, c));
+    BSS_TRY(launch_ip(h, ip_args(h, false)));   // gate on, no denominator floor: src/sss/idlma.py:200-207
+    h->y_valid = false;
+    return BSS_OK;
+}
+
+// src/sss/idlma.py:150-165; 'power' / False raise in the reference: the wrapper raises before calling
+int idlma_normalize(bss_handle* h) {
+    if (h->cfg.normalize != BSS_NORMALIZE_PROJECTION_BACK)
+        return bss_fail(h, BSS_EINVAL, "Not support normalization based on power. Choose 'power' or 'projection-back'");
+    return normalize_filter(h, 2.0);
+}
+
 int bss_loss_device(bss_handle* h) {
     const size_t BF = (size_t)h->B * h->F;
     double* result = h->lossbuf + BF;
@@ -318,6 +350,11 @@ int bss_loss_device(bss_handle* h) {
         MuArgs m = mu_args(h);
         const float expo = h->cfg.method == BSS_T_ILRMA ? 1.f : (float)(2.0 / h->cfg.domain);
         BSS_TRY(launch_ilrma_loss(h, m, expo, h->lossbuf));
+        return launch_loss_finish(h, h->lossbuf, h->logdet, coef, h->B, h->F, result);
+    }
+    if (h->cfg.method == BSS_GAUSS_IDLMA) {
+        if (!h->has_variance) return bss_fail(h, BSS_ESTATE, "GaussIDLMA: set the source variances (dnn_output) first");
+        BSS_TRY(launch_idlma_loss(h, h->X, h->Wf, h->iw, h->lossbuf, h->B, h->C, h->F, h->T, h->Tp));
         return launch_loss_finish(h, h->lossbuf, h->logdet, coef, h->B, h->F, result);
     }
     const int kind = h->cfg.method == BSS_AUX_LAPLACE_IVA ? 0 : 1;

@@ -110,6 +110,10 @@ int bss_set_state(bss_handle* h, int which, const void* src, int dtype) {
             BSS_TRY(put_rows(h, h->target, (const double*)src, (size_t)h->B * h->F, h->T, h->Tp));
             h->has_input = true;
             return BSS_OK;
+        case BSS_STATE_VARIANCE:
+            if (h->cfg.method != BSS_GAUSS_IDLMA) return bss_fail(h, BSS_EINVAL, "only GaussIDLMA takes external variances");
+            if (dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "variances are exchanged as float64");
+            return idlma_set_variance(h, (const double*)src);
     }
     return bss_fail(h, BSS_EINVAL, "state cannot be set");
 }

@@ -48,6 +48,8 @@ enum bss_method {
     BSS_AUX_GAUSS_IVA = 3,    /* src/bss/iva.py:621    AuxGaussIVA           */
     BSS_FAST_MNMF = 4,        /* src/bss/mnmf.py:637   FastMultichannelISNMF */
     BSS_IS_MNMF = 5,          /* src/bss/mnmf.py:116   MultichannelISNMF(author='Sawada'); `normalize` != 0 is normalize=True */
+    BSS_GAUSS_IDLMA = 6,      /* src/sss/idlma.py:88   GaussIDLMA: spatial model with source variances supplied by the caller
+                                 (BSS_STATE_VARIANCE, the output of the caller's DNN); update_once = update_space_model, bss_normalize = its normalisation */
     BSS_NMF_EUC = 10,         /* src/algorithm/nmf.py:150 EUCNMF             */
     BSS_NMF_KL = 11,          /* src/algorithm/nmf.py:209 KLNMF              */
     BSS_NMF_IS = 12,          /* src/algorithm/nmf.py:268 ISNMF              */
@@ -88,6 +90,7 @@ enum bss_dtype { BSS_F32 = 0, BSS_F64 = 1, BSS_C64 = 2, BSS_C128 = 3, BSS_I32 = 
  *   TARGET         (F,T)   real      NMF target
  *   COVARIANCE     (N,F,C,C) complex weighted covariances of the last spatial update (read only)
  *   GATE           (N,F)   int32     condition-number gate decisions of the last IP update (read only)
+ *   VARIANCE       (N,F,T) real      GaussIDLMA: R = dnn_output^(2/domain) (floored at eps on the device, src/sss/idlma.py:190) (write only)
  */
 enum bss_state {
     BSS_STATE_DEMIX_FILTER = 0,
@@ -99,7 +102,8 @@ enum bss_state {
     BSS_STATE_SPATIAL = 6,
     BSS_STATE_TARGET = 7,
     BSS_STATE_COVARIANCE = 8,
-    BSS_STATE_GATE = 9
+    BSS_STATE_GATE = 9,
+    BSS_STATE_VARIANCE = 10
 };
 
 typedef struct bss_config {
@@ -159,6 +163,10 @@ int bss_set_update_pair(bss_handle* h, int m, int n);
 /* Model.update_once(): src/bss/ilrma.py:286 / :814, src/bss/iva.py:469 / :702,
  * src/bss/mnmf.py:737, src/algorithm/nmf.py:182,241,302,329,397,461-595 */
 int bss_update_once(bss_handle* h);
+/* GaussIDLMA only: bss_update_once is update_space_model (src/sss/idlma.py:175-210: covariances from BSS_STATE_VARIANCE,
+ * gated IP sweep); bss_normalize is the normalisation tail of GaussIDLMA.update_once (src/sss/idlma.py:150-165,
+ * 'projection-back': W <- diag(scale) W).  The source-model half (the DNN) stays with the caller. */
+int bss_normalize(bss_handle* h);
 /* n_iter x update_once without returning to the host in between (the `for idx in
  * range(iteration)` loop of __call__, src/bss/ilrma.py:233, with recordable_loss=False and no
  * callbacks); advances the IP2 pair schedule itself */

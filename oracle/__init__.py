@@ -18,4 +18,4 @@ against the known-answer loss values of SURVEY.md Appendix D.  The resulting
 fixtures are committed under `tests/golden/`.
 """
 
-from . import core, ilrma, auxiva, fastmnmf, nmf, synth  # noqa: F401
+from . import core, ilrma, auxiva, fastmnmf, nmf, synth  # noqa: F401  (mnmf, idlma: imported where used)

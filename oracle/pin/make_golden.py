@@ -7,6 +7,7 @@ them to ~1e-10, and stores inputs + reference outputs as tests/golden/<case>.npz
 has no /root/reference: tests only ever read the committed .npz files.
 
     python oracle/pin/make_golden.py            # regenerate everything
+    python oracle/pin/make_golden.py idlma      # only the GaussIDLMA fixtures
 """
 import json
 import os
@@ -32,7 +33,9 @@ from algorithm.nmf import EUCNMF, KLNMF, ISNMF, tNMF, CauchyNMF  # noqa: E402
 from algorithm.projection_back import projection_back  # noqa: E402
 from utils.utils_linalg import parallel_sort  # noqa: E402
 
-from oracle import core, ilrma, auxiva, fastmnmf, mnmf, nmf, synth  # noqa: E402
+from sss.idlma import GaussIDLMA  # noqa: E402
+
+from oracle import core, ilrma, auxiva, fastmnmf, idlma, mnmf, nmf, synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 TOL = 1e-9
@@ -127,6 +130,38 @@ def case_auxiva(name, kind, C, F, T, spatial, iters):
     check(name, got, want, TOL if spatial not in ('IP2', 'pairwise') else 1e-7)
     save(name, dict(model='AuxLaplaceIVA' if kind == 'laplace' else 'AuxGaussIVA',
                     algorithm_spatial=spatial, iteration=iters), {'X': X, 'W0': W0}, want)
+
+
+# ------------------------------------------------------------------------------- Gauss-IDLMA
+
+def case_idlma(name, C, F, T, domain, iters):
+    """GaussIDLMA with the toy DNN of oracle/synth.py (the reference needs a torch module, src/sss/idlma.py:216-224)."""
+    X = synth.mix2(C, F, T, K=2, seed=4)
+    dnn = synth.toy_dnn()
+    model = GaussIDLMA(domain=domain, normalize='projection-back')
+    out = model(X, iteration=iters, dnn=dnn)
+    want = {'output': out, 'demix_filter': model.demix_filter, 'dnn_output': model.dnn_output.astype(np.float64),
+            'loss': np.array(model.loss, dtype=np.float64)}
+    o_out, st, o_loss = idlma.run(X, synth.dnn_as_callable(dnn), iteration=iters, domain=domain)
+    check(name, {'output': o_out, 'demix_filter': st['W'], 'dnn_output': st['dnn_output'], 'loss': np.array(o_loss)}, want, 1e-7)
+    # update_space_model alone from a given state (what the C entry point bss_update_once covers)
+    model2 = GaussIDLMA(domain=domain, normalize='projection-back')
+    model2.input = X
+    model2._reset(dnn=dnn)
+    rng = np.random.default_rng(21)
+    R0 = (10 ** rng.uniform(-3, 1, size=(C, F, T))).astype(np.float32)
+    R0[0, 0, :3] = 0.0
+    model2.dnn_output = R0.copy()
+    model2.update_space_model()
+    st2 = idlma.init_state(X)
+    st2['dnn_output'] = R0.copy()
+    idlma.update_space_model(st2, domain)
+    check(name + ' (space model)', {'W1': st2['W']}, {'W1': model2.demix_filter}, 1e-9)
+    want['space_W1'] = model2.demix_filter.copy()
+    want['space_loss1'] = np.float64(model2.compute_negative_loglikelihood())
+    e = abs(idlma.negative_loglikelihood(st2, domain) - want['space_loss1']) / abs(want['space_loss1'])
+    assert e < 1e-6, e   # the reference takes log(R) in float32
+    save(name, dict(model='GaussIDLMA', domain=domain, iteration=iters, dnn='oracle.synth.toy_dnn()'), {'X': X, 'R0': R0}, want)
 
 
 # ------------------------------------------------------------------------------- FastMNMF
@@ -302,6 +337,10 @@ def case_seeded_dropin():
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     print("pinning oracle against /root/reference (numpy {}), tol {:g}".format(np.__version__, TOL))
+    if sys.argv[1:] == ['idlma']:    # regenerate just these fixtures
+        case_idlma('idlma_gauss_d2', 3, 17, 40, 2, 3)
+        case_idlma('idlma_gauss_d1', 2, 17, 40, 1, 3)
+        return
     case_primitives()
     case_seeded_dropin()
     case_ilrma('ilrma_ip_power_d2', 4, 33, 48, 2, 'IP', 'power', 2, 4)
@@ -320,6 +359,8 @@ def main():
     case_auxiva('auxiva_laplace_iss', 'laplace', 3, 17, 40, 'ISS', 3)
     case_auxiva('auxiva_gauss_iss', 'gauss', 2, 17, 40, 'ISS', 3)
     case_auxiva('auxiva_laplace_ip2', 'laplace', 3, 17, 40, 'IP2', 4)
+    case_idlma('idlma_gauss_d2', 3, 17, 40, 2, 3)
+    case_idlma('idlma_gauss_d1', 2, 17, 40, 1, 3)
     case_fastmnmf('fastmnmf_m3n3', 3, 3, 17, 40, 2, 3)
     case_fastmnmf('fastmnmf_m4n2', 4, 2, 9, 32, 3, 2)
     case_mnmf_sawada('mnmf_sawada_c2n2', 2, 2, 9, 24, 3, 3)

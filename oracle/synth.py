@@ -57,3 +57,30 @@ def spectrogram(F, T, seed=0):
     rng = np.random.default_rng(seed)
     Z = (rng.standard_normal((F, T)) ** 2 + rng.standard_normal((F, T)) ** 2) / 2
     return Z.astype(np.float32).astype(np.float64)
+
+
+def toy_dnn(gain=0.8, bias=1e-3, width=5):
+    """A deterministic stand-in for the source-model DNN of GaussIDLMA (src/sss/idlma.py:212-226): a torch module with one
+    parameter that smooths each (source, bin) row over `width` frames.  Tests and the pinning script build it identically."""
+    import torch
+
+    class ToyDNN(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gain = torch.nn.Parameter(torch.tensor([float(gain)]))
+
+        def forward(self, x):
+            y = torch.nn.functional.avg_pool1d(x, kernel_size=width, stride=1, padding=width // 2, count_include_pad=False)
+            return self.gain * y + bias
+
+    return ToyDNN()
+
+
+def dnn_as_callable(module):
+    """What the reference's estimate_by_dnn does around the module (src/sss/idlma.py:216-224): float32 in, float32 out."""
+    import torch
+
+    def call(a):
+        with torch.no_grad():
+            return module(torch.Tensor(a)).cpu().numpy()
+    return call

@@ -138,3 +138,19 @@ def test_mnmf_sawada(name, closed_form):
     assert rel(st['H'], o['spatial']) < tol
     assert rel(st['Z'], o['latent']) < tol and rel(st['T'], o['basis']) < tol and rel(st['V'], o['activation']) < tol
     assert rel(loss, o['loss']) < tol
+
+
+@pytest.mark.parametrize('name', ['idlma_gauss_d2', 'idlma_gauss_d1'])
+def test_idlma(name):
+    """GaussIDLMA (src/sss/idlma.py) with the toy DNN; the DNN runs in torch float32 on this machine's CPU, so 1e-6."""
+    from oracle import idlma, synth
+    meta, i, o = load_golden(name)
+    dnn = synth.dnn_as_callable(synth.toy_dnn())
+    out, st, loss = idlma.run(i['X'], dnn, iteration=meta['iteration'], domain=meta['domain'])
+    assert rel(out, o['output']) < 1e-6 and rel(st['W'], o['demix_filter']) < 1e-6
+    assert rel(st['dnn_output'], o['dnn_output']) < 1e-6 and rel(loss, o['loss']) < 1e-6
+    st2 = idlma.init_state(i['X'])
+    st2['dnn_output'] = i['R0'].copy()
+    idlma.update_space_model(st2, meta['domain'])
+    assert rel(st2['W'], o['space_W1']) < TOL
+    assert abs(idlma.negative_loglikelihood(st2, meta['domain']) - o['space_loss1']) < 1e-6 * abs(o['space_loss1'])
