@@ -182,7 +182,7 @@ void bss_destroy(bss_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->X,   h->Y,    h->W,     h->Wf,    h->basis, h->basis2, h->act,     h->latent, h->U,      h->Cx,
                     h->gate, h->flags, h->pw,   h->scale, h->wfr,   h->wraw,   h->order,   h->logdet, h->aux,    h->G2x,
-                    h->part, h->iw,   h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
+                    h->part, h->iw, h->P, h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
                     h->nz,   h->nt,   h->nv,    h->npart, h->loss_hist, h->G2, h->beff, h->aeff, h->praw,
                     h->sH,   h->sZ,   h->sT,    h->sV,    h->sStat, h->sPart, h->sAcc};
     for (void* p : bufs)

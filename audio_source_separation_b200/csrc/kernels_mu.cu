@@ -88,7 +88,8 @@ struct MuParams {
 // KFIX: n_basis == KC at compile time (basis row in registers, one item per bin);
 // otherwise n_basis is a run-time value, an item is a (bin, chunk of KC basis vectors) pair.
 // CACHE: CTA-contiguous bin ranges with the activation rows in shared memory (see cov_kernel).
-template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE>
+// WP: also store the source power |y|^2 of every frame as float bin tiles (a.Pout) for the activation update.
+template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE, bool WP>
 __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const MuParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,6 +162,12 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
             float2 P[C];
             frame_power2<C, FROM_Y>(xv, w, P);
             const int t = tbase + tt;
+            if (WP) {
+                // tile_off(N, Tp, n, t) inside this 128-frame block: rows of nf floats
+                float* pd = a.Pout + ((size_t)st.cons.item * N * Tp + (size_t)tbase * N + tt);
+#pragma unroll
+                for (int n = 0; n < N; ++n) *reinterpret_cast<float2*>(pd + n * nf) = P[n];
+            }
 #pragma unroll
             for (int n = 0; n < N; ++n) {
                 const float* v = CACHE ? vcache + voff + n * K * Tp + t : vrow + (size_t)n * K * Tp + t;
@@ -233,15 +240,18 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
     }
 }
 
-template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE>
+template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE, bool WP = false>
 int launch_mu_basis_c(bss_handle* h, const MuParams& p, const StreamPlan& sp, size_t smem_bytes) {
+    if constexpr (!WP && KFIX && !FROM_Y) {
+        if (p.a.Pout) return launch_mu_basis_c<C, KC, KFIX, FROM_Y, CACHE, true>(h, p, sp, smem_bytes);
+    }
     static bool attr_done = false;
     if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          h->max_smem));
         attr_done = true;
     }
-    mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
+    mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE, WP><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
@@ -465,12 +475,15 @@ __global__ void __launch_bounds__(256) pack_bin_params_kernel(const cf* Wf, cons
     reinterpret_cast<float*>(out)[idx] = v;
 }
 
-template <int C, int KC, bool FROM_Y>
+// FROM_P: the ring carries the float power tiles the basis kernel stored (a.Pin) instead of the mixture: no filter in the
+// packed parameters, no y = W x, half the bytes.
+template <int C, int KC, bool FROM_Y, bool FROM_P>
 __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_stream_kernel(const ActParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MuArgs& a = p.a;
     constexpr int N = C;
+    constexpr int STG = FROM_P ? 2 * ACT_STAGES : ACT_STAGES;   // half-size stages: twice as many in flight
     const int item = (int)blockIdx.x * ACT_WARPS + warp;
     if (item >= p.n_items) return;
     // item -> (b, chunk, block), block fastest: the warps of a CTA read consecutive 4 KB blocks of the same bins
@@ -483,16 +496,20 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
     const int Tp = a.Tp;
     const int blk0 = s * BSS_XSLAB;
     const int L = min(BSS_XSLAB, Tp - blk0);          // frames of this block (even)
-    const uint32_t blk_bytes = (uint32_t)(C * L * 8);
-    const cf* src0 = (FROM_Y ? a.Y : a.X) + (size_t)b * a.F * C * Tp + (size_t)blk0 * C;
+    constexpr int ESZ = FROM_P ? 4 : 8;               // bytes per tile element
+    const uint32_t blk_bytes = (uint32_t)(C * L * ESZ);
+    const size_t bin_bytes = (size_t)C * Tp * ESZ;
+    const unsigned char* src0 = (FROM_P ? reinterpret_cast<const unsigned char*>(a.Pin)
+                                        : reinterpret_cast<const unsigned char*>(FROM_Y ? a.Y : a.X)) +
+                                ((size_t)b * a.F * C * Tp + (size_t)blk0 * C) * ESZ;
     const unsigned char* par0 = p.pbin + (size_t)b * a.F * p.pb_stride;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * ACT_STAGES;
-    unsigned char* ring = smem + 128 + (size_t)warp * ACT_STAGES * p.stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * STG;
+    unsigned char* ring = smem + ACT_WARPS * STG * 8 + (size_t)warp * STG * p.stage_bytes;   // barriers first (128 / 256 B)
     const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < ACT_STAGES; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < STG; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
@@ -503,7 +520,7 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(blk_bytes + (uint32_t)p.pb_stride)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(src0 + (size_t)f * C * Tp), "r"(blk_bytes), "r"(bar)
+                         "l"(src0 + (size_t)f * bin_bytes), "r"(blk_bytes), "r"(bar)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + p.par_off),
                          "l"(par0 + (size_t)f * p.pb_stride), "r"((uint32_t)p.pb_stride), "r"(bar)
@@ -512,9 +529,9 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
     };
     int fp = f_begin, pstage = 0;
 #pragma unroll 1
-    for (int i = 0; i < ACT_STAGES - 1 && fp < f_end; ++i, ++fp) {
+    for (int i = 0; i < STG - 1 && fp < f_end; ++i, ++fp) {
         issue(fp, pstage);
-        pstage = pstage + 1 == ACT_STAGES ? 0 : pstage + 1;
+        pstage = pstage + 1 == STG ? 0 : pstage + 1;
     }
 
     // loop invariants of this lane: activation values of its frame pairs (two pairs per 128-frame block)
@@ -540,7 +557,7 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
         if (fp < f_end) {
             issue(fp, pstage);
             ++fp;
-            pstage = pstage + 1 == ACT_STAGES ? 0 : pstage + 1;
+            pstage = pstage + 1 == STG ? 0 : pstage + 1;
         }
         {
             const uint32_t bar = bars_sa + 8u * (uint32_t)cstage;
@@ -558,9 +575,9 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
         const unsigned char* stage = ring + (size_t)cstage * p.stage_bytes;
         const cf* xs = reinterpret_cast<const cf*>(stage);
         const float2* wf = reinterpret_cast<const float2*>(stage + p.par_off);
-        const float* tb = reinterpret_cast<const float*>(stage + p.par_off) + (FROM_Y ? 0 : C * C * 2);
+        const float* tb = reinterpret_cast<const float*>(stage + p.par_off) + (FROM_Y || FROM_P ? 0 : C * C * 2);
         float2 w[C][C];
-        if (!FROM_Y) {
+        if (!FROM_Y && !FROM_P) {
 #pragma unroll
             for (int n = 0; n < C; ++n)
 #pragma unroll
@@ -575,11 +592,16 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
         for (int j = 0; j < 2; ++j) {
             const int tt = 2 * lane + 64 * j;
             if (tt < L) {
-                float4 xv[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * L + tt);
                 float2 P[C];
-                frame_power2<C, FROM_Y>(xv, w, P);
+                if (FROM_P) {
+#pragma unroll
+                    for (int n = 0; n < N; ++n) P[n] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage) + n * L + tt);
+                } else {
+                    float4 xv[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * L + tt);
+                    frame_power2<C, FROM_Y>(xv, w, P);
+                }
 #pragma unroll
                 for (int n = 0; n < N; ++n) {
                     float2 tv = make_float2(0.f, 0.f);
@@ -599,7 +621,7 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
             }
         }
         __syncwarp();
-        if (++cstage == ACT_STAGES) {
+        if (++cstage == STG) {
             cstage = 0;
             cphase ^= 1u;
         }
@@ -621,25 +643,29 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
 }
 
 // host: choose the number of bin chunks so that the warps fill the machine in whole waves
-template <int C, int KC, bool FROM_Y>
+template <int C, int KC, bool FROM_Y, bool FROM_P = false>
 int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done) {
+    if constexpr (!FROM_P && !FROM_Y) {
+        if (a.Pin) return launch_mu_act_stream<C, KC, FROM_Y, true>(h, a, n_chunks_out, done);
+    }
     *done = false;
     ActParams p{};
     p.a = a;
     p.n_blocks = (a.Tp + BSS_XSLAB - 1) / BSS_XSLAB;
     const int blk_frames = a.Tp < BSS_XSLAB ? a.Tp : BSS_XSLAB;
-    p.pb_stride = round_up((FROM_Y ? 0 : C * C * 8) + C * KC * 4, 16);
-    p.par_off = (uint32_t)round_up(C * blk_frames * 8, 16);
+    p.pb_stride = round_up((FROM_Y || FROM_P ? 0 : C * C * 8) + C * KC * 4, 16);
+    p.par_off = (uint32_t)round_up(C * blk_frames * (FROM_P ? 4 : 8), 16);
     p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
-    const size_t smem_bytes = 128 + (size_t)ACT_WARPS * ACT_STAGES * p.stage_bytes;
+    constexpr int STG = FROM_P ? 2 * ACT_STAGES : ACT_STAGES;
+    const size_t smem_bytes = (size_t)ACT_WARPS * STG * 8 + (size_t)ACT_WARPS * STG * p.stage_bytes;
     if (smem_bytes > (size_t)h->max_smem) return BSS_OK;   // fall back to the direct-load kernel
     static bool attr_done = false;
     if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_stream_kernel<C, KC, FROM_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_stream_kernel<C, KC, FROM_Y, FROM_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_done = true;
     }
     int ctas_per_sm = 1;
-    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_act_stream_kernel<C, KC, FROM_Y>, ACT_WARPS * 32, smem_bytes));
+    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_act_stream_kernel<C, KC, FROM_Y, FROM_P>, ACT_WARPS * 32, smem_bytes));
     if (ctas_per_sm < 1) return BSS_OK;
     const long long slots = (long long)h->n_sm * ctas_per_sm * ACT_WARPS;
     const long long per_chunk = (long long)a.B * p.n_blocks;
@@ -674,10 +700,10 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
     p.part = h->part;
     const long long words = (long long)a.B * a.F * (p.pb_stride >> 2);
     pack_bin_params_kernel<<<(unsigned)cdiv(words, 256), 256, 0, h->stream>>>(a.Wf, a.basis, (unsigned char*)h->staging, a.B, C, C, a.F,
-                                                                             KC, p.pb_stride, FROM_Y ? 0 : 1);
+                                                                             KC, p.pb_stride, FROM_Y || FROM_P ? 0 : 1);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
-    mu_act_stream_kernel<C, KC, FROM_Y><<<(unsigned)cdiv(n_items, ACT_WARPS), ACT_WARPS * 32, smem_bytes, h->stream>>>(p);
+    mu_act_stream_kernel<C, KC, FROM_Y, FROM_P><<<(unsigned)cdiv(n_items, ACT_WARPS), ACT_WARPS * 32, smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     if (n_chunks_out) *n_chunks_out = p.n_chunks;

@@ -1,6 +1,8 @@
 // update_once / loss / separate of the determined methods (Gauss-ILRMA, t-ILRMA, AuxIVA):
 // which kernels run, in which order, on which buffers.  All work is queued on h->stream; nothing
 // here synchronises with the host.
+#include <cstdlib>
+
 #include "methods.h"
 
 namespace {
@@ -89,16 +91,37 @@ IpArgs ip_args(bss_handle* h, bool want_power) {
     return a;
 }
 
+// The basis update computes |y|^2 = |W x|^2 of every frame anyway; with n_basis == 2 (the compile-time-K kernels) it hands
+// them to the activation update as float tiles (half the bytes of X, no second demixing).  Same arithmetic, same values:
+// results are bit-identical to the two-pass form (BSSGPU_NO_POWER_HANDOFF=1 selects it, for A/B measurements).
+bool power_handoff(bss_handle* h) {
+    static const bool disabled = getenv("BSSGPU_NO_POWER_HANDOFF") != nullptr;
+    if (disabled || is_iss(h) || h->K != 2) return false;
+    if (((size_t)h->N * h->Tp) % 4 != 0) return false;   // 16-byte bulk copies of float rows
+    if (!h->P) {
+        if (cudaMalloc((void**)&h->P, (size_t)h->B * h->F * h->N * h->Tp * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            h->P = nullptr;
+            return false;   // not enough memory for the hand-off buffer: stream X twice
+        }
+    }
+    return true;
+}
+
 int source_model(bss_handle* h, int sel_m, int sel_n) {
     MuArgs m = mu_args(h);
     m.sel_m = sel_m;
     m.sel_n = sel_n;
+    const bool handoff = power_handoff(h);
+    if (handoff) m.Pout = h->P;
     BSS_TRY(launch_mu_basis(h, m));
     float* t = h->basis;
     h->basis = h->basis2;
     h->basis2 = t;
     m.basis = h->basis;
     m.basis_out = h->basis2;
+    m.Pout = nullptr;
+    if (handoff) m.Pin = h->P;
     return launch_mu_act(h, m, h->act);
 }
 
