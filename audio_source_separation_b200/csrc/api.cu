@@ -338,6 +338,26 @@ static bool graph_capable(const bss_handle* h) {
     return true;
 }
 
+// FNV-1a over every device pointer (and scratch size) a captured update_once of the determined methods can reference, in
+// their current roles (basis / basis2 swap every iteration).  0 = this configuration is re-captured on every call.
+static uint64_t graph_signature(const bss_handle* h) {
+    if (h->cfg.method > BSS_AUX_GAUSS_IVA || h->cfg.partitioning) return 0;
+    const void* ptrs[] = {h->X, h->Y, h->W, h->Wf, h->basis, h->basis2, h->act, h->U, h->Cx, h->gate, h->flags, h->pw, h->scale,
+                          h->wfr, h->wraw, h->order, h->logdet, h->aux, h->G2x, h->part, h->iw, h->P, h->lossbuf, h->staging};
+    uint64_t s = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) {
+        for (int i = 0; i < 8; ++i) {
+            s ^= (v >> (8 * i)) & 0xffu;
+            s *= 1099511628211ull;
+        }
+    };
+    for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+    mix((uint64_t)h->part_elems);
+    mix((uint64_t)h->staging_bytes);
+    mix((uint64_t)(uintptr_t)h->stream);
+    return s ? s : 1;
+}
+
 int bss_run(bss_handle* h, int n_iter) {
     if (!h || n_iter < 0) return BSS_EINVAL;
     BSS_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -347,29 +367,44 @@ int bss_run(bss_handle* h, int n_iter) {
     // eager warm-up: every scratch buffer reaches its final size and every kernel attribute is set before the capture
     BSS_TRY(run_eager(h, kWarm));
     n_iter -= kWarm;
-    if (h->graph_exec) {
-        cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
-        h->graph_exec = nullptr;
-    }
-    cudaGraph_t graph = nullptr;
-    const int64_t l0 = h->launches;
-    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-        cudaGetLastError();
-        return run_eager(h, n_iter);
-    }
-    const int rc_cap = run_eager(h, kPerGraph);
-    const cudaError_t e_end = cudaStreamEndCapture(h->stream, &graph);
-    const int64_t per_graph = h->launches - l0;
-    h->launches = l0;   // nothing of the capture has executed
+    // A handle that is used for job after job (batch.py keeps its handles) replays the graph it already has as long as
+    // the captured kernel arguments still describe the current state: instantiating and destroying an executable graph
+    // per call costs host time and synchronises with the other handles' streams, which serialised the pipelined
+    // end-to-end job (profiles/r5b_e2e_timeline.txt).
+    const uint64_t sig = graph_signature(h);
     cudaGraphExec_t exec = nullptr;
-    if (rc_cap != BSS_OK || e_end != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
-        cudaGetLastError();
-        if (graph) cudaGraphDestroy(graph);
-        if (rc_cap != BSS_OK) return rc_cap;
-        return run_eager(h, n_iter);
+    int64_t per_graph = 0;
+    if (h->graph_exec && sig != 0 && sig == h->graph_sig) {
+        exec = (cudaGraphExec_t)h->graph_exec;
+        per_graph = h->graph_launches;
+    } else {
+        if (h->graph_exec) {
+            cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+            h->graph_exec = nullptr;
+            h->graph_sig = 0;
+        }
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = h->launches;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return run_eager(h, n_iter);
+        }
+        const int rc_cap = run_eager(h, kPerGraph);
+        const cudaError_t e_end = cudaStreamEndCapture(h->stream, &graph);
+        per_graph = h->launches - l0;
+        h->launches = l0;   // nothing of the capture has executed
+        if (rc_cap != BSS_OK || e_end != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            if (rc_cap != BSS_OK) return rc_cap;
+            return run_eager(h, n_iter);
+        }
+        cudaGraphDestroy(graph);
+        h->graph_exec = exec;
+        h->graph_launches = per_graph;
+        // the capture itself may have grown a scratch buffer: sign the state the kernels were actually recorded with
+        h->graph_sig = graph_signature(h) == sig ? sig : 0;
     }
-    cudaGraphDestroy(graph);
-    h->graph_exec = exec;
     const int reps = n_iter / kPerGraph;
     for (int r = 0; r < reps; ++r) BSS_CUDA(h, cudaGraphLaunch(exec, h->stream));
     h->launches += per_graph * reps;

@@ -27,6 +27,8 @@ struct bss_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     void* graph_exec = nullptr;    // cudaGraphExec_t of the last captured pair of iterations (bss_run)
+    uint64_t graph_sig = 0;        // signature of every device pointer the captured kernels were given (0: do not reuse)
+    int64_t graph_launches = 0;    // kernel launches per replay of graph_exec
     std::string err;
 
     bool has_input = false;

@@ -124,3 +124,43 @@ def test_graph_replay_equals_eager_loop(cuda_device, kind, monkeypatch):
     assert graph_launches == eager_launches          # replayed launches are counted
     for a, b in zip(graph_states, eager_states):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('kind', ['ilrma_ip', 'ilrma_iss', 'auxiva'])
+def test_cached_graph_serves_later_runs(cuda_device, kind, monkeypatch):
+    """A handle that runs job after job keeps its executable graph (bss_run re-captures only when the device pointers the
+    kernels were recorded with changed, e.g. after an odd number of iterations swapped the basis buffers): the 2nd, 3rd,
+    4th job on one handle must be bit-identical to the same job run eagerly on a fresh handle."""
+    from audio_source_separation_b200 import _lib
+    C, F, T, K = 3, 40, 150, 2
+    X = synth.mix2(C, F, T, seed=4)
+    X2 = synth.mix2(C, F, T, seed=5)
+    T0 = np.random.default_rng(1).random((C, F, K))
+    V0 = np.random.default_rng(2).random((C, K, T))
+    common = dict(n_batch=1, n_channels=C, n_sources=C, n_bins=F, n_frames=T, n_basis=K)
+
+    def make():
+        if kind == 'auxiva':
+            return _lib.Handle(method=_lib.AUX_LAPLACE_IVA, normalize=_lib.NORMALIZE_NONE, **common)
+        return _lib.Handle(method=_lib.GAUSS_ILRMA, spatial=_lib.SPATIAL_ISS if kind == 'ilrma_iss' else _lib.SPATIAL_IP, **common)
+
+    def job(h, x, n_iter):
+        h.set_input(x)
+        h.reset_spatial()
+        if kind != 'auxiva':
+            h.set_state(_lib.STATE_BASIS, T0, np.float64)
+            h.set_state(_lib.STATE_ACTIVATION, V0, np.float64)
+        h.run(n_iter)
+        return h.separate((C, F, T), np.complex128, projection_back=True)
+
+    monkeypatch.delenv('BSSGPU_NO_GRAPH', raising=False)
+    h = make()
+    plan = [(X, 24), (X2, 24), (X, 25), (X2, 24), (X, 24)]   # the odd job leaves the basis buffers swapped
+    got = [job(h, x, n) for x, n in plan]
+    h.close()
+    monkeypatch.setenv('BSSGPU_NO_GRAPH', '1')
+    for (x, n), g in zip(plan, got):
+        e = make()
+        want = job(e, x, n)
+        e.close()
+        assert np.array_equal(g, want)

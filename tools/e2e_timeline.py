@@ -23,15 +23,15 @@ T0 = rng.random((B, C, F, K)); V0 = rng.random((B, C, K, T))
 spans = [shard_range(B, i, P) for i in range(P)]
 hs = [_lib.Handle(method=_lib.GAUSS_ILRMA, spatial=0, normalize=1, n_batch=hi - lo, n_channels=C, n_sources=C, n_bins=F, n_frames=T,
                   n_basis=K, stream_priority=-(P - 1 - i)) for i, (lo, hi) in enumerate(spans)]
-for rep in range(2):
+for rep in range(3):
     marks = [dict() for _ in range(P)]
     t0 = time.perf_counter()
     def job(i):
         lo, hi = spans[i]; h = hs[i]; m = marks[i]
-        h.set_input_ptr(X[lo:hi].ctypes.data, _lib.C64); m['input'] = time.perf_counter() - t0
-        h.reset_spatial()
+        h.reset_spatial()   # same order as batch.py: small uploads first
         h.set_state(_lib.STATE_BASIS, T0[lo:hi], np.float64)
         h.set_state(_lib.STATE_ACTIVATION, V0[lo:hi], np.float64); m['state'] = time.perf_counter() - t0
+        h.set_input_ptr(X[lo:hi].ctypes.data, _lib.C64); m['input'] = time.perf_counter() - t0
         h.run(steps); m['queued'] = time.perf_counter() - t0
         h.synchronize(); m['loop'] = time.perf_counter() - t0
         h.separate_into(Y[lo:hi].ctypes.data, _lib.C64, True); m['out'] = time.perf_counter() - t0
