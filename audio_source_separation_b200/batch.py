@@ -72,7 +72,8 @@ class BatchedGaussILRMA:
 
     def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline=4):
         """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
-        `out` (B,N,F,T) complex64 (allocated when None).  The batch is cut into `pipeline` sub-batches, each with its own
+        `out` (B,N,F,T) complex64 (allocated when None).  The batch is cut into `pipeline` sub-batches (a count, or a list of
+        sub-batch sizes), each with its own
         handle and CUDA stream and driven by its own host thread, so the host->device copy of one sub-batch and the
         device->host copy of another overlap the update loop of the rest (pass pinned arrays to make the copies
         asynchronous).  Mixtures are independent, so the result is identical to one undivided call."""
@@ -87,8 +88,18 @@ class BatchedGaussILRMA:
             basis = np.random.rand(B, C, F, K)
         if activation is None:
             activation = np.random.rand(B, C, K, T)
-        n_parts = max(1, min(int(pipeline), B))
-        spans = [shard_range(B, i, n_parts) for i in range(n_parts)]
+        if isinstance(pipeline, (list, tuple)):
+            # explicit sub-batch sizes, e.g. small first and last ones: the first upload and the last download are the only
+            # copies nothing overlaps
+            sizes = [int(v) for v in pipeline if int(v) > 0]
+            if sum(sizes) != B:
+                raise ValueError("pipeline sizes {} do not add up to the batch size {}".format(sizes, B))
+            n_parts = len(sizes)
+            edges = np.concatenate(([0], np.cumsum(sizes)))
+            spans = [(int(edges[i]), int(edges[i + 1])) for i in range(n_parts)]
+        else:
+            n_parts = max(1, min(int(pipeline), B))
+            spans = [shard_range(B, i, n_parts) for i in range(n_parts)]
         if not hasattr(self, '_parts') or len(self._parts) != n_parts:
             self._parts = [None] * n_parts
         x_dtype = _lib.C64 if X.dtype == np.complex64 else _lib.C128

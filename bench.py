@@ -283,9 +283,12 @@ def run_gpu_arm(args):
     # ---- end to end through the host API ---------------------------------------------------------
     x_np, y_np = x_host.numpy(), y_host.numpy()
 
+    pipeline = [int(v) for v in str(args.pipeline).split(',')]
+    pipeline = pipeline[0] if len(pipeline) == 1 else pipeline
+
     def e2e_job():
         # the public whole-job call: 4 sub-batches on 4 streams so that H2D / D2H overlap the update loop
-        model.separate_batch(x_np, y_np, iteration=steps, basis=T0, activation=V0, pipeline=args.pipeline)
+        model.separate_batch(x_np, y_np, iteration=steps, basis=T0, activation=V0, pipeline=pipeline)
 
     e2e_job()   # warm (allocations of the sub-batch handles and staging buffers)
     e2e_runs = []
@@ -366,7 +369,8 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=64, help='mixtures per GPU')
-    ap.add_argument('--pipeline', type=int, default=4, help='sub-batches of the end-to-end job (copy/compute overlap)')
+    ap.add_argument('--pipeline', default='4', help='sub-batches of the end-to-end job (copy/compute overlap): a count, or '
+                    'comma-separated sub-batch sizes adding up to --batch')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
