@@ -283,8 +283,12 @@ def run_gpu_arm(args):
     # ---- end to end through the host API ---------------------------------------------------------
     x_np, y_np = x_host.numpy(), y_host.numpy()
 
-    pipeline = [int(v) for v in str(args.pipeline).split(',')]
-    pipeline = pipeline[0] if len(pipeline) == 1 else pipeline
+    if args.pipeline == 'ramp':
+        from audio_source_separation_b200.batch import ramp_sizes
+        pipeline = ramp_sizes(B)
+    else:
+        pipeline = [int(v) for v in str(args.pipeline).split(',')]
+        pipeline = pipeline[0] if len(pipeline) == 1 else pipeline
 
     def e2e_job():
         # the public whole-job call: 4 sub-batches on 4 streams so that H2D / D2H overlap the update loop
@@ -340,9 +344,9 @@ def run_gpu_arm(args):
                        "batch_per_gpu": B, "global_batch": world * B, "step": "one update_once over the resident batch",
                        "l2": "inputs larger than L2 ({:.2f} GB per GPU per pass): no flush".format(B * 8 * C * F * T / 1e9),
                        "storage": "complex64/float32 tensors, float64 per-bin solves",
-                       "e2e_job": "one BatchedGaussILRMA.separate_batch call ({} pipelined sub-batches): H2D batch from pinned memory "
+                       "e2e_job": "one BatchedGaussILRMA.separate_batch call (pipelined sub-batches: {}): H2D batch from pinned memory "
                                   "+ {} iterations + separate/projection-back + D2H to pinned memory; bytes amortised per "
-                                  "iteration".format(args.pipeline, steps),
+                                  "iteration".format(pipeline, steps),
                        "gather_ms": gather_ms},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": x_host.numel() * 8 / steps,
@@ -369,8 +373,8 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=64, help='mixtures per GPU')
-    ap.add_argument('--pipeline', default='4', help='sub-batches of the end-to-end job (copy/compute overlap): a count, or '
-                    'comma-separated sub-batch sizes adding up to --batch')
+    ap.add_argument('--pipeline', default='ramp', help="sub-batches of the end-to-end job (copy/compute overlap): 'ramp' "
+                    "(batch.ramp_sizes), a count, or comma-separated sub-batch sizes adding up to --batch")
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

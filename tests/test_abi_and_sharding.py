@@ -120,3 +120,14 @@ def test_gather_outputs_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count('ok') == 2
+
+
+def test_ramp_sizes_cover_the_batch():
+    """Sub-batch sizes of the pipelined whole-job call (batch.ramp_sizes): positive, add up, small at both ends."""
+    from audio_source_separation_b200.batch import ramp_sizes
+    for n in list(range(1, 70)) + [100, 512, 1000]:
+        sizes = ramp_sizes(n)
+        assert sum(sizes) == n and all(v > 0 for v in sizes)
+        if n >= 32:
+            assert len(sizes) == 7 and sizes[0] <= sizes[3] and sizes[-1] <= sizes[3]
+    assert ramp_sizes(64) == [4, 8, 12, 16, 12, 8, 4]

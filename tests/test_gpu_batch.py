@@ -35,7 +35,7 @@ def test_batch_equals_loop(cuda_device, C, F, T, K):
     assert rel(out, singles) < 1e-5
     assert batched.compute_negative_loglikelihood().shape == (B,)
     # pipelined whole-job call: sub-batches on their own streams, complex64 output
-    for pipeline in (1, 2, 5):
+    for pipeline in (1, 2, 5, [1, 3, 1], 'ramp'):
         out2 = BatchedGaussILRMA(n_basis=K).separate_batch(X.astype(np.complex64), iteration=n_iter, basis=T0, activation=V0,
                                                           pipeline=pipeline)
         assert out2.dtype == np.complex64 and rel(out2, singles) < 1e-5
