@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, cons
 // parameters (demixing filter rows and basis values, one more bulk copy), so the loop body touches only shared
 // memory and registers.  The lane's activation values are loop invariants (registers), as are its accumulators.
 constexpr int ACT_STAGES = 4;
+constexpr int ACT_STAGES_P = 6;   // power tiles (FROM_P): 6 x 2 KB per warp, four CTAs per SM (the kernel is latency bound: occupancy first)
 constexpr int ACT_WARPS = 4;
 
 struct ActParams {
@@ -478,12 +479,12 @@ __global__ void __launch_bounds__(256) pack_bin_params_kernel(const cf* Wf, cons
 // FROM_P: the ring carries the float power tiles the basis kernel stored (a.Pin) instead of the mixture: no filter in the
 // packed parameters, no y = W x, half the bytes.
 template <int C, int KC, bool FROM_Y, bool FROM_P>
-__global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_stream_kernel(const ActParams p) {
+__global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? (FROM_P ? 4 : 3) : 1)) mu_act_stream_kernel(const ActParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MuArgs& a = p.a;
     constexpr int N = C;
-    constexpr int STG = FROM_P ? 2 * ACT_STAGES : ACT_STAGES;   // half-size stages: twice as many in flight
+    constexpr int STG = FROM_P ? ACT_STAGES_P : ACT_STAGES;   // half-size stages: more of them in flight
     const int item = (int)blockIdx.x * ACT_WARPS + warp;
     if (item >= p.n_items) return;
     // item -> (b, chunk, block), block fastest: the warps of a CTA read consecutive 4 KB blocks of the same bins
@@ -656,7 +657,7 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
     p.pb_stride = round_up((FROM_Y || FROM_P ? 0 : C * C * 8) + C * KC * 4, 16);
     p.par_off = (uint32_t)round_up(C * blk_frames * (FROM_P ? 4 : 8), 16);
     p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
-    constexpr int STG = FROM_P ? 2 * ACT_STAGES : ACT_STAGES;
+    constexpr int STG = FROM_P ? ACT_STAGES_P : ACT_STAGES;
     const size_t smem_bytes = (size_t)ACT_WARPS * STG * 8 + (size_t)ACT_WARPS * STG * p.stage_bytes;
     if (smem_bytes > (size_t)h->max_smem) return BSS_OK;   // fall back to the direct-load kernel
     static bool attr_done = false;
