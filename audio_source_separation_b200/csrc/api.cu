@@ -13,8 +13,6 @@ static thread_local std::string g_create_error;
 namespace {
 
 bool is_nmf(int m) { return m >= BSS_NMF_EUC && m <= BSS_NMF_CAUCHY; }
-bool is_ilrma(int m) { return m == BSS_GAUSS_ILRMA || m == BSS_T_ILRMA; }
-bool is_iva(int m) { return m == BSS_AUX_LAPLACE_IVA || m == BSS_AUX_GAUSS_IVA; }
 
 template <typename T>
 int dev_alloc(bss_handle* h, T** p, size_t n) {

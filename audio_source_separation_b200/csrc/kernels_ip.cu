@@ -44,27 +44,12 @@ __device__ __forceinline__ double row_power(const Mat<C>& W, const Mat<C>& Cx, i
     return q.x;
 }
 
-// L1 prefetch of n doubles starting at p (first and last cache line: the packed matrices are at most 512 B)
-__device__ __forceinline__ void prefetch_l1_span(const double* p, int n) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    if (n > 16) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 16));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 48));
-    }
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + n - 1));
-}
-
+// (an L1 prefetch of the later U_n at the top of the sweep did not move the 173 us of the 64-mixture case: profiles/r5f_*)
 template <int C>
 __global__ void __launch_bounds__(64) ip_sweep_kernel(const IpArgs a) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)a.B * a.F) return;
     const int b = (int)(idx / a.F), f = (int)(idx - (long long)b * a.F);
-    // The sweep is serial in n and every U_n is loaded right where it is needed: at 255 registers (7 warps per SM) that
-    // load latency is exposed (ncu: long_scoreboard is the top stall).  Pull the later matrices into L1 now.
-#pragma unroll
-    for (int n = 1; n < C; ++n) prefetch_l1_span(a.U + (((size_t)b * C + n) * a.F + f) * C * C, C * C);
-    if (a.pw) prefetch_l1_span(a.Cx + (size_t)idx * C * C, C * C);
     Mat<C> W;
     load_w<C>(a.W + (size_t)idx * C * C, W);
     bool singular = false;

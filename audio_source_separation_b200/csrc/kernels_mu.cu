@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, cons
 // parameters (demixing filter rows and basis values, one more bulk copy), so the loop body touches only shared
 // memory and registers.  The lane's activation values are loop invariants (registers), as are its accumulators.
 constexpr int ACT_STAGES = 4;
-constexpr int ACT_STAGES_P = 6;   // power tiles (FROM_P): 6 x 2 KB per warp, four CTAs per SM (the kernel is latency bound: occupancy first)
+constexpr int ACT_STAGES_P = 8;   // power tiles (FROM_P): half-size stages, twice as many in flight.  Four CTAs per SM with six stages
+                                  // (128 registers, small spills) measured slower: 299 vs 285 us (profiles/r5f_*)
 constexpr int ACT_WARPS = 4;
 
 struct ActParams {
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(256) pack_bin_params_kernel(const cf* Wf, cons
 // FROM_P: the ring carries the float power tiles the basis kernel stored (a.Pin) instead of the mixture: no filter in the
 // packed parameters, no y = W x, half the bytes.
 template <int C, int KC, bool FROM_Y, bool FROM_P>
-__global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? (FROM_P ? 4 : 3) : 1)) mu_act_stream_kernel(const ActParams p) {
+__global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_stream_kernel(const ActParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MuArgs& a = p.a;
