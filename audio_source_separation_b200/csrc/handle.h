@@ -60,7 +60,7 @@ struct bss_handle {
     double2* G2x = nullptr;        // [B][F][N][C] cross covariance Y X^H / T (ISS filter recovery)
     float* part = nullptr;         // partial sums of the cross-bin reductions
     size_t part_elems = 0;
-    float* P = nullptr;            // [B][F] tiles of N x Tp floats: source power handed from the basis to the activation update
+    float* P = nullptr;            // [B][128-frame block][F][N][128] floats: source power handed from the basis to the activation update
     float* iw = nullptr;           // [B][F][NW][Tp] explicit inverse weights (generic covariance path)
     double* lossbuf = nullptr;     // [B][F] per-bin loss terms + [B] results
     void* staging = nullptr;       // device staging for host <-> device layout conversion
@@ -247,8 +247,8 @@ struct MuArgs {
     float nu, eps;
     int sel_m, sel_n;     // >= 0: pairwise source model, only these two sources move
     float* raw;           // non-null: basis kernel stores the raw (num, den) sums [B][N][F][K][2] instead of updating
-    float* Pout;          // non-null (n_basis == 2, filter-based): the basis kernel also stores |y|^2 as float bin tiles
-                          // [B][F] x tile(N rows, Tp) (block-interleaved like X), half the bytes of X ...
+    float* Pout;          // non-null (n_basis == 2, filter-based): the basis kernel also stores |y|^2 as float tiles, block-major
+                          // [B][128-frame block][F][N][128] (a block's bins are consecutive), half the bytes of X ...
     const float* Pin;     // ... which the activation kernel then streams instead of X: no second y = W x, half the traffic
 };
 int launch_mu_basis(bss_handle* h, const MuArgs& a);

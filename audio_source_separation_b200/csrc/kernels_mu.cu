@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
             frame_power2<C, FROM_Y>(xv, w, P);
             const int t = tbase + tt;
             if (WP) {
-                // tile_off(N, Tp, n, t) inside this 128-frame block: rows of nf floats
-                float* pd = a.Pout + ((size_t)st.cons.item * N * Tp + (size_t)tbase * N + tt);
+                // block-major power tiles [b][128-frame block][f][N rows of nf floats] (stride N * 128 floats per bin): for a
+                // fixed block the bins are consecutive, so the activation kernel fetches several bins with one bulk copy
+                float* pd = a.Pout + ((((size_t)b * ((Tp + MU_SLAB - 1) / MU_SLAB) + tbase / MU_SLAB) * a.F + f) * N * MU_SLAB + tt);
 #pragma unroll
                 for (int n = 0; n < N; ++n) *reinterpret_cast<float2*>(pd + n * nf) = P[n];
             }
@@ -444,8 +445,8 @@ __global__ void __launch_bounds__(256) mu_act_finish_kernel(const MuArgs a, cons
 // parameters (demixing filter rows and basis values, one more bulk copy), so the loop body touches only shared
 // memory and registers.  The lane's activation values are loop invariants (registers), as are its accumulators.
 constexpr int ACT_STAGES = 4;
-constexpr int ACT_STAGES_P = 8;   // power tiles (FROM_P): half-size stages, twice as many in flight.  Four CTAs per SM with six stages
-                                  // (128 registers, small spills) measured slower: 299 vs 285 us (profiles/r5f_*)
+constexpr int ACT_BINS_P = 2;     // power tiles (FROM_P): bins per ring stage (one bulk copy).  More resident warps instead (four CTAs
+                                  // per SM, six single-bin stages, 128 registers) measured slower: 299 vs 285 us (profiles/r5f_*)
 constexpr int ACT_WARPS = 4;
 
 struct ActParams {
@@ -485,10 +486,13 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MuArgs& a = p.a;
     constexpr int N = C;
-    constexpr int STG = FROM_P ? ACT_STAGES_P : ACT_STAGES;   // half-size stages: more of them in flight
+    constexpr int STG = ACT_STAGES;
+    // bins per ring stage.  A 2 KB power block per bulk copy is too small: the per-copy cost of the copy engine, not DRAM,
+    // bounded the kernel (4.0 TB/s); the power tiles are laid out block-major so that one copy brings two bins.
+    constexpr int G = FROM_P ? ACT_BINS_P : 1;
     const int item = (int)blockIdx.x * ACT_WARPS + warp;
     if (item >= p.n_items) return;
-    // item -> (b, chunk, block), block fastest: the warps of a CTA read consecutive 4 KB blocks of the same bins
+    // item -> (b, chunk, block), block fastest: the warps of a CTA read consecutive blocks of the same bins
     const int s = item % p.n_blocks;
     const int bc = item / p.n_blocks;
     const int chunk = bc % p.n_chunks;
@@ -500,14 +504,15 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
     const int L = min(BSS_XSLAB, Tp - blk0);          // frames of this block (even)
     constexpr int ESZ = FROM_P ? 4 : 8;               // bytes per tile element
     const uint32_t blk_bytes = (uint32_t)(C * L * ESZ);
-    const size_t bin_bytes = (size_t)C * Tp * ESZ;
-    const unsigned char* src0 = (FROM_P ? reinterpret_cast<const unsigned char*>(a.Pin)
-                                        : reinterpret_cast<const unsigned char*>(FROM_Y ? a.Y : a.X)) +
-                                ((size_t)b * a.F * C * Tp + (size_t)blk0 * C) * ESZ;
+    // distance between the blocks of consecutive bins, and where bin f_begin's block starts
+    const size_t bin_bytes = FROM_P ? (size_t)C * BSS_XSLAB * ESZ : (size_t)C * Tp * ESZ;
+    const unsigned char* src0 =
+        FROM_P ? reinterpret_cast<const unsigned char*>(a.Pin) + ((size_t)b * p.n_blocks + s) * a.F * bin_bytes
+               : reinterpret_cast<const unsigned char*>(FROM_Y ? a.Y : a.X) + ((size_t)b * a.F * C * Tp + (size_t)blk0 * C) * ESZ;
     const unsigned char* par0 = p.pbin + (size_t)b * a.F * p.pb_stride;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * STG;
-    unsigned char* ring = smem + ACT_WARPS * STG * 8 + (size_t)warp * STG * p.stage_bytes;   // barriers first (128 / 256 B)
+    unsigned char* ring = smem + ACT_WARPS * STG * 8 + (size_t)warp * STG * p.stage_bytes;   // barriers first
     const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring);
     if (lane == 0) {
 #pragma unroll
@@ -515,23 +520,26 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
         mbar_fence_init();
     }
     __syncwarp();
+    // one stage = the blocks of up to G consecutive bins (bin g at g * bin_bytes) followed by their packed parameters
     auto issue = [&](int f, int stage) {
         if (lane == 0) {
+            const int g = min(G, f_end - f);
             const uint32_t bar = bars_sa + 8u * (uint32_t)stage;
             const uint32_t dst = ring_sa + (uint32_t)stage * p.stage_bytes;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(blk_bytes + (uint32_t)p.pb_stride)
-                         : "memory");
+            const uint32_t tile_bytes = (uint32_t)(g - 1) * (uint32_t)bin_bytes + blk_bytes;
+            const uint32_t par_bytes = (uint32_t)g * (uint32_t)p.pb_stride;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes + par_bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(src0 + (size_t)f * bin_bytes), "r"(blk_bytes), "r"(bar)
+                         "l"(src0 + (size_t)f * bin_bytes), "r"(tile_bytes), "r"(bar)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + p.par_off),
-                         "l"(par0 + (size_t)f * p.pb_stride), "r"((uint32_t)p.pb_stride), "r"(bar)
+                         "l"(par0 + (size_t)f * p.pb_stride), "r"(par_bytes), "r"(bar)
                          : "memory");
         }
     };
     int fp = f_begin, pstage = 0;
 #pragma unroll 1
-    for (int i = 0; i < STG - 1 && fp < f_end; ++i, ++fp) {
+    for (int i = 0; i < STG - 1 && fp < f_end; ++i, fp += G) {
         issue(fp, pstage);
         pstage = pstage + 1 == STG ? 0 : pstage + 1;
     }
@@ -555,10 +563,10 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
     int cstage = 0;
     uint32_t cphase = 0;
 #pragma unroll 1
-    for (int f = f_begin; f < f_end; ++f) {
+    for (int f = f_begin; f < f_end; f += G) {
         if (fp < f_end) {
             issue(fp, pstage);
-            ++fp;
+            fp += G;
             pstage = pstage + 1 == STG ? 0 : pstage + 1;
         }
         {
@@ -574,50 +582,56 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
                     : "memory");
             }
         }
-        const unsigned char* stage = ring + (size_t)cstage * p.stage_bytes;
-        const cf* xs = reinterpret_cast<const cf*>(stage);
-        const float2* wf = reinterpret_cast<const float2*>(stage + p.par_off);
-        const float* tb = reinterpret_cast<const float*>(stage + p.par_off) + (FROM_Y || FROM_P ? 0 : C * C * 2);
-        float2 w[C][C];
-        if (!FROM_Y && !FROM_P) {
+        const unsigned char* stage0 = ring + (size_t)cstage * p.stage_bytes;
+        const int g_n = G == 1 ? 1 : min(G, f_end - f);
+#pragma unroll 1
+        for (int g = 0; g < g_n; ++g) {
+            const unsigned char* stage = stage0 + (size_t)g * bin_bytes;
+            const unsigned char* par = stage0 + p.par_off + g * p.pb_stride;
+            const cf* xs = reinterpret_cast<const cf*>(stage);
+            const float2* wf = reinterpret_cast<const float2*>(par);
+            const float* tb = reinterpret_cast<const float*>(par) + (FROM_Y || FROM_P ? 0 : C * C * 2);
+            float2 w[C][C];
+            if (!FROM_Y && !FROM_P) {
 #pragma unroll
-            for (int n = 0; n < C; ++n)
+                for (int n = 0; n < C; ++n)
 #pragma unroll
-                for (int c = 0; c < C; ++c) w[n][c] = wf[n * C + c];
-        }
-        float tk[N][KC];
+                    for (int c = 0; c < C; ++c) w[n][c] = wf[n * C + c];
+            }
+            float tk[N][KC];
 #pragma unroll
-        for (int n = 0; n < N; ++n)
+            for (int n = 0; n < N; ++n)
 #pragma unroll
-            for (int kk = 0; kk < KC; ++kk) tk[n][kk] = tb[n * KC + kk];
+                for (int kk = 0; kk < KC; ++kk) tk[n][kk] = tb[n * KC + kk];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int tt = 2 * lane + 64 * j;
-            if (tt < L) {
-                float2 P[C];
-                if (FROM_P) {
+            for (int j = 0; j < 2; ++j) {
+                const int tt = 2 * lane + 64 * j;
+                if (tt < L) {
+                    float2 P[C];
+                    if (FROM_P) {
 #pragma unroll
-                    for (int n = 0; n < N; ++n) P[n] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage) + n * L + tt);
-                } else {
-                    float4 xv[C];
+                        for (int n = 0; n < N; ++n) P[n] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(stage) + n * L + tt);
+                    } else {
+                        float4 xv[C];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * L + tt);
-                    frame_power2<C, FROM_Y>(xv, w, P);
-                }
+                        for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * L + tt);
+                        frame_power2<C, FROM_Y>(xv, w, P);
+                    }
 #pragma unroll
-                for (int n = 0; n < N; ++n) {
-                    float2 tv = make_float2(0.f, 0.f);
+                    for (int n = 0; n < N; ++n) {
+                        float2 tv = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tk[n][kk], tk[n][kk]), tv);
-                    tv.x = fmaxf(tv.x, a.eps);
-                    tv.y = fmaxf(tv.y, a.eps);
-                    float2 sa, sb;
-                    mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
+                        for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tk[n][kk], tk[n][kk]), tv);
+                        tv.x = fmaxf(tv.x, a.eps);
+                        tv.y = fmaxf(tv.y, a.eps);
+                        float2 sa, sb;
+                        mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
 #pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) {
-                        const float2 t2 = make_float2(tk[n][kk], tk[n][kk]);
-                        num[j][n][kk] = __ffma2_rn(sa, t2, num[j][n][kk]);
-                        den[j][n][kk] = __ffma2_rn(sb, t2, den[j][n][kk]);
+                        for (int kk = 0; kk < KC; ++kk) {
+                            const float2 t2 = make_float2(tk[n][kk], tk[n][kk]);
+                            num[j][n][kk] = __ffma2_rn(sa, t2, num[j][n][kk]);
+                            den[j][n][kk] = __ffma2_rn(sb, t2, den[j][n][kk]);
+                        }
                     }
                 }
             }
@@ -656,9 +670,11 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
     p.n_blocks = (a.Tp + BSS_XSLAB - 1) / BSS_XSLAB;
     const int blk_frames = a.Tp < BSS_XSLAB ? a.Tp : BSS_XSLAB;
     p.pb_stride = round_up((FROM_Y || FROM_P ? 0 : C * C * 8) + C * KC * 4, 16);
-    p.par_off = (uint32_t)round_up(C * blk_frames * (FROM_P ? 4 : 8), 16);
-    p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
-    constexpr int STG = FROM_P ? ACT_STAGES_P : ACT_STAGES;
+    constexpr int G = FROM_P ? ACT_BINS_P : 1;
+    // FROM_P: G bins per stage at the fixed block-major stride (C * 128 floats), then their G parameter records
+    p.par_off = FROM_P ? (uint32_t)(G * C * BSS_XSLAB * 4) : (uint32_t)round_up(C * blk_frames * 8, 16);
+    p.stage_bytes = (uint32_t)round_up((int)p.par_off + G * p.pb_stride, 128);
+    constexpr int STG = ACT_STAGES;
     const size_t smem_bytes = (size_t)ACT_WARPS * STG * 8 + (size_t)ACT_WARPS * STG * p.stage_bytes;
     if (smem_bytes > (size_t)h->max_smem) return BSS_OK;   // fall back to the direct-load kernel
     static bool attr_done = false;

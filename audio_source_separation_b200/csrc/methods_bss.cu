@@ -99,7 +99,8 @@ bool power_handoff(bss_handle* h) {
     if (disabled || is_iss(h) || h->K != 2) return false;
     if (((size_t)h->N * h->Tp) % 4 != 0) return false;   // 16-byte bulk copies of float rows
     if (!h->P) {
-        if (cudaMalloc((void**)&h->P, (size_t)h->B * h->F * h->N * h->Tp * sizeof(float)) != cudaSuccess) {
+        const size_t n_blocks = ((size_t)h->Tp + BSS_XSLAB - 1) / BSS_XSLAB;   // block-major: [B][block][F][N][128]
+        if (cudaMalloc((void**)&h->P, (size_t)h->B * n_blocks * h->F * h->N * BSS_XSLAB * sizeof(float)) != cudaSuccess) {
             cudaGetLastError();
             h->P = nullptr;
             return false;   // not enough memory for the hand-off buffer: stream X twice
