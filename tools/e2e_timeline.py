@@ -7,11 +7,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from audio_source_separation_b200 import _lib
-from audio_source_separation_b200.batch import shard_range
+from audio_source_separation_b200.batch import shard_range, ramp_sizes
 from audio_source_separation_b200._model import parse_spatial, parse_normalize
 
 B, C, F, T, K = 64, 4, 2049, 512, 2
-P = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+arg = sys.argv[1] if len(sys.argv) > 1 else 'ramp'   # 'ramp', a count, or comma-separated sub-batch sizes
 steps = 100
 x = torch.empty((B, C, F, T), dtype=torch.complex64, pin_memory=True)
 x.numpy()[:] = (np.random.default_rng(0).standard_normal((B, C, F, T), dtype=np.float32)
@@ -20,7 +20,13 @@ y = torch.empty((B, C, F, T), dtype=torch.complex64, pin_memory=True)
 X, Y = x.numpy(), y.numpy()
 rng = np.random.default_rng(7)
 T0 = rng.random((B, C, F, K)); V0 = rng.random((B, C, K, T))
-spans = [shard_range(B, i, P) for i in range(P)]
+if arg == 'ramp' or ',' in arg:
+    sizes = ramp_sizes(B) if arg == 'ramp' else [int(v) for v in arg.split(',')]
+    edges = np.concatenate(([0], np.cumsum(sizes)))
+    spans = [(int(edges[i]), int(edges[i + 1])) for i in range(len(sizes))]
+else:
+    spans = [shard_range(B, i, int(arg)) for i in range(int(arg))]
+P = len(spans)
 hs = [_lib.Handle(method=_lib.GAUSS_ILRMA, spatial=0, normalize=1, n_batch=hi - lo, n_channels=C, n_sources=C, n_bins=F, n_frames=T,
                   n_basis=K, stream_priority=-(P - 1 - i)) for i, (lo, hi) in enumerate(spans)]
 for rep in range(3):
