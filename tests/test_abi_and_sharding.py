@@ -131,3 +131,24 @@ def test_ramp_sizes_cover_the_batch():
         if n >= 32:
             assert len(sizes) == 7 and sizes[0] <= sizes[3] and sizes[-1] <= sizes[3]
     assert ramp_sizes(64) == [4, 8, 12, 16, 12, 8, 4]
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints exactly one JSON line with the
+    keys the driver reads; one timed update_once per worker keeps this to a few seconds."""
+    import json
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['unit'] == 'iterations/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # a non-zero rank of a torchrun launch prints nothing and exits 0
+    env['RANK'] = '1'
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ''
