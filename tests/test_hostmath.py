@@ -130,6 +130,41 @@ def test_ip_gate_decisions_near_threshold(hm):
     assert np.array_equal(Wg[~ok, 0], W0[~ok, 0])
 
 
+@pytest.mark.parametrize('C', [2, 3, 4, 5, 8])
+def test_ip_gate_sweep_of_condition_numbers(hm, C):
+    """The gate takes a determinant-based shortcut when cond_2 is certainly below the threshold and the exact route
+    otherwise: over twelve decades of condition numbers (dense around 1e12, several singular-value profiles) the decision
+    must be numpy's `cond(W U) < 1e12`, and the updated rows must agree with the oracle wherever the gate passes."""
+    rng = np.random.default_rng(40 + C)
+    exps = np.concatenate((np.linspace(0, 11, 23), np.linspace(11.0, 13.0, 41), np.linspace(13, 15, 5)))
+    F = len(exps)
+    U = np.empty((C, F, C, C), dtype=np.complex128)
+    for n in range(C):
+        for f in range(F):
+            Q, _ = np.linalg.qr(_rand_c(rng, C, C))
+            lo = 10.0 ** -exps[f]
+            if n % 3 == 0:       # one small singular value
+                sv = np.concatenate((np.ones(C - 1), [lo]))
+            elif n % 3 == 1:     # geometric spread
+                sv = lo ** (np.arange(C) / (C - 1))
+            else:                # one large singular value
+                sv = np.concatenate(([1.0], np.full(C - 1, lo)))
+            U[n, f] = (Q * (sv * 10.0 ** rng.uniform(-3, 3))) @ Q.conj().T
+    W0 = np.tile(np.eye(C, dtype=np.complex128), (F, 1, 1))
+    Wg, gate_g, n_sing = _sweep(hm, W0, U)
+    assert n_sing == 0
+    # row 0 sees W = I, so its matrix is U[0] itself; the later rows see whatever the earlier updates left
+    cond0 = np.linalg.cond(U[0])
+    clear = np.abs(np.log10(cond0) - 12.0) > 1e-3      # numpy's own SVD is only good to ~1e-4 relative at cond 1e12
+    assert np.array_equal(gate_g[0][clear], (cond0 < 1e12)[clear])
+    Wo = W0.copy()
+    gate_o = core.ip_rows(Wo, U)
+    agree = gate_g == gate_o
+    assert agree[0][clear].all()
+    ok = gate_o[0] & gate_g[0] & (cond0 < 1e9)
+    assert rel(Wg[ok, 0], Wo[ok, 0]) < 1e-6
+
+
 @pytest.mark.parametrize('C', [2, 3, 4])
 def test_hermitian_eig_and_riccati(hm, C):
     """Jacobi eigen-decomposition and the closed-form Riccati solution the IS-MNMF spatial update runs, against
