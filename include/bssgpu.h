@@ -18,6 +18,13 @@
  *   - a handle is bound to one device and one stream and is not thread-safe
  *   - dtype arguments select the HOST element type; device storage is complex64/float32 for
  *     the big tensors and float64 for the per-bin linear algebra (demixing filters, covariances)
+ *
+ * Environment switches (measurement aids; every alternative gives the same results, the first two bit for bit)
+ *   BSSGPU_NO_GRAPH=1           bss_run queues every iteration eagerly instead of replaying a CUDA graph
+ *   BSSGPU_NO_POWER_HANDOFF=1   the activation update recomputes |W x|^2 from the mixture instead of reading the
+ *                               powers the basis update stored (n_basis == 2)
+ *   BSSGPU_NO_CLUSTER=1         NMF runs its per-phase kernels instead of the single cluster launch
+ *   BSSGPU_NO_MMA=1             FastMNMF covariances / spatial update on CUDA cores instead of tensor cores
  */
 #ifndef BSSGPU_H
 #define BSSGPU_H
