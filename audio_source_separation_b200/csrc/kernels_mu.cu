@@ -480,7 +480,10 @@ __global__ void __launch_bounds__(256) pack_bin_params_kernel(const cf* Wf, cons
 
 // FROM_P: the ring carries the float power tiles the basis kernel stored (a.Pin) instead of the mixture: no filter in the
 // packed parameters, no y = W x, half the bytes.
-template <int C, int KC, bool FROM_Y, bool FROM_P>
+// GAUSS2: Gauss source model with domain 2 (mode 0, p_exp == 2) decided at compile time: the run-time dispatch of mu_stats2,
+// inlined once per source and frame pair with its powf / Student-t branches, tripled the code of the loop body and showed up
+// as instruction-fetch and branch stalls in the (latency bound) power-tile form.
+template <int C, int KC, bool FROM_Y, bool FROM_P, bool GAUSS2>
 __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_stream_kernel(const ActParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -625,7 +628,12 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
                         tv.x = fmaxf(tv.x, a.eps);
                         tv.y = fmaxf(tv.y, a.eps);
                         float2 sa, sb;
-                        mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
+                        if (GAUSS2) {
+                            sb = rcp2(tv);
+                            sa = __fmul2_rn(P[n], __fmul2_rn(sb, sb));   // the p_exp == 2 branch of mu_stats2
+                        } else {
+                            mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
+                        }
 #pragma unroll
                         for (int kk = 0; kk < KC; ++kk) {
                             const float2 t2 = make_float2(tk[n][kk], tk[n][kk]);
@@ -659,10 +667,13 @@ __global__ void __launch_bounds__(ACT_WARPS * 32, (C <= 4 ? 3 : 1)) mu_act_strea
 }
 
 // host: choose the number of bin chunks so that the warps fill the machine in whole waves
-template <int C, int KC, bool FROM_Y, bool FROM_P = false>
+template <int C, int KC, bool FROM_Y, bool FROM_P = false, bool GAUSS2 = false>
 int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done) {
     if constexpr (!FROM_P && !FROM_Y) {
-        if (a.Pin) return launch_mu_act_stream<C, KC, FROM_Y, true>(h, a, n_chunks_out, done);
+        if (a.Pin) {
+            if (a.mode == 0 && a.p_exp == 2.f) return launch_mu_act_stream<C, KC, FROM_Y, true, true>(h, a, n_chunks_out, done);
+            return launch_mu_act_stream<C, KC, FROM_Y, true, false>(h, a, n_chunks_out, done);
+        }
     }
     *done = false;
     ActParams p{};
@@ -679,11 +690,11 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
     if (smem_bytes > (size_t)h->max_smem) return BSS_OK;   // fall back to the direct-load kernel
     static bool attr_done = false;
     if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_stream_kernel<C, KC, FROM_Y, FROM_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_act_stream_kernel<C, KC, FROM_Y, FROM_P, GAUSS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_done = true;
     }
     int ctas_per_sm = 1;
-    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_act_stream_kernel<C, KC, FROM_Y, FROM_P>, ACT_WARPS * 32, smem_bytes));
+    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_act_stream_kernel<C, KC, FROM_Y, FROM_P, GAUSS2>, ACT_WARPS * 32, smem_bytes));
     if (ctas_per_sm < 1) return BSS_OK;
     const long long slots = (long long)h->n_sm * ctas_per_sm * ACT_WARPS;
     const long long per_chunk = (long long)a.B * p.n_blocks;
@@ -721,7 +732,7 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
                                                                              KC, p.pb_stride, FROM_Y || FROM_P ? 0 : 1);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
-    mu_act_stream_kernel<C, KC, FROM_Y, FROM_P><<<(unsigned)cdiv(n_items, ACT_WARPS), ACT_WARPS * 32, smem_bytes, h->stream>>>(p);
+    mu_act_stream_kernel<C, KC, FROM_Y, FROM_P, GAUSS2><<<(unsigned)cdiv(n_items, ACT_WARPS), ACT_WARPS * 32, smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     if (n_chunks_out) *n_chunks_out = p.n_chunks;
