@@ -89,7 +89,8 @@ struct MuParams {
 // otherwise n_basis is a run-time value, an item is a (bin, chunk of KC basis vectors) pair.
 // CACHE: CTA-contiguous bin ranges with the activation rows in shared memory (see cov_kernel).
 // WP: also store the source power |y|^2 of every frame as float bin tiles (a.Pout) for the activation update.
-template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE, bool WP>
+// GAUSS2 (only together with WP): mode 0 with p_exp == 2 decided at compile time, see mu_act_stream_kernel.
+template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE, bool WP, bool GAUSS2 = false>
 __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const MuParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,7 +196,12 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
                 tv.x = fmaxf(tv.x, a.eps);
                 tv.y = fmaxf(tv.y, a.eps);
                 float2 sa, sb;
-                mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
+                if (GAUSS2) {
+                    sb = rcp2(tv);
+                    sa = __fmul2_rn(P[n], __fmul2_rn(sb, sb));   // the p_exp == 2 branch of mu_stats2
+                } else {
+                    mu_stats2(a.mode, P[n], tv, a.p_exp, a.nu, sa, sb);
+                }
 #pragma unroll
                 for (int kk = 0; kk < KC; ++kk) {
                     num[n][kk] = __ffma2_rn(sa, vk[kk], num[n][kk]);
@@ -241,18 +247,21 @@ __global__ void __launch_bounds__(MU_MAX_WARPS * 32, 1) mu_basis_kernel(const Mu
     }
 }
 
-template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE, bool WP = false>
+template <int C, int KC, bool KFIX, bool FROM_Y, bool CACHE, bool WP = false, bool GAUSS2 = false>
 int launch_mu_basis_c(bss_handle* h, const MuParams& p, const StreamPlan& sp, size_t smem_bytes) {
     if constexpr (!WP && KFIX && !FROM_Y) {
-        if (p.a.Pout) return launch_mu_basis_c<C, KC, KFIX, FROM_Y, CACHE, true>(h, p, sp, smem_bytes);
+        if (p.a.Pout) {
+            if (p.a.mode == 0 && p.a.p_exp == 2.f) return launch_mu_basis_c<C, KC, KFIX, FROM_Y, CACHE, true, true>(h, p, sp, smem_bytes);
+            return launch_mu_basis_c<C, KC, KFIX, FROM_Y, CACHE, true, false>(h, p, sp, smem_bytes);
+        }
     }
     static bool attr_done = false;
     if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         h->max_smem));
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE, WP, GAUSS2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_done = true;
     }
-    mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE, WP><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
+    mu_basis_kernel<C, KC, KFIX, FROM_Y, CACHE, WP, GAUSS2><<<sp.grid, sp.wpc * 32, smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
