@@ -194,3 +194,29 @@ class FakeILRMAHandle:
 
     def close(self):
         self.calls.append('close')
+
+
+class FakeAuxIVAHandle(FakeILRMAHandle):
+    """AuxLaplaceIVA / AuxGaussIVA (IP, IP2, ISS) answered by oracle/auxiva.py; same call semantics as above, no source model."""
+    instances = []
+
+    def __init__(self, **cfg):
+        assert cfg['method'] in (_lib.AUX_LAPLACE_IVA, _lib.AUX_GAUSS_IVA)
+        self.cfg = cfg
+        self.kind = 'laplace' if cfg['method'] == _lib.AUX_LAPLACE_IVA else 'gauss'
+        self.spatial = self.SPATIAL[cfg['spatial']]
+        self.calls = []
+        self.X = self.W = self.Y = self.T = self.V = None
+        self.pair = None
+        FakeAuxIVAHandle.instances.append(self)
+
+    def update_once(self):
+        from oracle import auxiva as o_auxiva
+        self.calls.append('update_once')
+        st = self._state()
+        o_auxiva.update_once(st, self.kind, self.spatial, self.cfg['eps'], self.cfg['threshold'])
+        self._take(st)
+
+    def loss(self):
+        from oracle import auxiva as o_auxiva
+        return np.array([o_auxiva.negative_loglikelihood(self._state(), self.kind, self.cfg['eps'])])
