@@ -24,7 +24,11 @@ ALG_MM, ALG_ME, ALG_NAIVE, ALG_MM_FAST = 0, 1, 2, 3
 F32, F64, C64, C128, I32 = 0, 1, 2, 3, 4
 # enum bss_state
 (STATE_DEMIX_FILTER, STATE_ESTIMATION, STATE_BASIS, STATE_ACTIVATION, STATE_LATENT, STATE_DIAGONALIZER,
- STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE, STATE_VARIANCE) = range(11)
+ STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE, STATE_VARIANCE, STATE_ORDER, STATE_EIGVAL) = range(13)
+# enum bss_option / bss_info
+OPT_IP_KERNEL = 0
+IP_AUTO, IP_THREAD_PER_BIN, IP_LANE_GROUP, IP_FUSED, IP_PAIRWISE = 0, 1, 2, 3, 4
+INFO_IP_KERNEL, INFO_GRAPH_REPLAYS, INFO_LAUNCHES = 0, 1, 2
 
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64,
            np.dtype(np.complex128): C128, np.dtype(np.int32): I32}
@@ -68,6 +72,9 @@ SIGNATURES = {
     'bss_separate_device': (_i, [_vp, _vp, _i]),
     'bss_separate_waveform': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     'bss_compute_demix_filter': (_i, [_vp]),
+    'bss_set_option': (_i, [_vp, _i, _i]),
+    'bss_get_info': (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
+    'bss_least_squares_map': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'bss_weighted_covariance': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'bss_ip_update': (_i, [_i, _i, _i, _vp, _vp, _vp, _d, _i, _d]),
     'bss_projection_back_scale': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
@@ -252,6 +259,14 @@ class Handle:
     def compute_demix_filter(self):
         self._check(self._lib.bss_compute_demix_filter(self._h))
 
+    def set_option(self, option, value):
+        self._check(self._lib.bss_set_option(self._h, int(option), int(value)))
+
+    def get_info(self, what):
+        out = ctypes.c_int64()
+        self._check(self._lib.bss_get_info(self._h, int(what), ctypes.byref(out)))
+        return int(out.value)
+
     # measurement --------------------------------------------------------------------------------
     def timer_begin(self):
         self._check(self._lib.bss_timer_begin(self._h))
@@ -305,6 +320,21 @@ def projection_back_scale(x, w, reference_id=0, device=0):
     code = lib.bss_projection_back_scale(device, C, F, T, _ptr(x), _ptr(w), int(reference_id), _ptr(scale))
     check_static(code, 'bss_projection_back_scale')
     return scale
+
+
+def least_squares_map(a, b, device=0):
+    """Per-bin M_f = A_f B_f^H (B_f B_f^H)^-1; a (Ra,F,T), b (Rb,F,T) -> (Ra,Rb,F) complex128."""
+    lib = load()
+    a = as_host(a, np.complex128)
+    b = as_host(b, np.complex128)
+    if a.ndim != 3 or b.ndim != 3 or a.shape[1:] != b.shape[1:]:
+        raise ValueError("expected (rows, n_bins, n_frames) arrays with equal bins and frames, got {} and {}".format(a.shape, b.shape))
+    Ra, F, T = a.shape
+    Rb = b.shape[0]
+    out = np.empty((Ra, Rb, F), dtype=np.complex128)
+    code = lib.bss_least_squares_map(device, Ra, Rb, F, T, _ptr(a), _ptr(b), _ptr(out))
+    check_static(code, 'bss_least_squares_map')
+    return out
 
 
 def demix(x, w, device=0):

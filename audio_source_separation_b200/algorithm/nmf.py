@@ -75,7 +75,7 @@ class NMFbase(DeviceModel):
         cfg = self._config()
         self._open_handle(tuple(sorted(cfg.items())), **cfg)
         target = self.target
-        token = (id(target), target.shape, target.dtype.str)
+        token = (id(target), target.shape, target.dtype.str, self._fingerprint(np.asarray(target)))
         if self._input_token != token:
             self._handle.set_state(_lib.STATE_TARGET, target, np.float64)
             self.__dict__['_input_token'] = token
@@ -97,6 +97,7 @@ class NMFbase(DeviceModel):
 
         self.basis = np.random.rand(n_bins, n_basis)
         self.activation = np.random.rand(n_basis, n_frames)
+        self.__dict__['_input_token'] = None   # every __call__ re-reads the target, like the reference
 
     def update(self, iteration=100):
         """`iteration` x (update_once, criterion) without leaving the device (src/algorithm/nmf.py:165-174)."""

@@ -15,6 +15,14 @@ EPS = 1e-12
 THRESHOLD = 1e+12
 
 
+def _check_presets(B, C, F, T, K, demix_filter=None, basis=None, activation=None):
+    """The C ABI carries no lengths: a wrongly shaped preset would make the library read past the end of the host buffer."""
+    for name, value, shape in (('demix_filter', demix_filter, (B, F, C, C)), ('basis', basis, (B, C, F, K)),
+                               ('activation', activation, (B, C, K, T))):
+        if value is not None and tuple(np.shape(value)) != shape:
+            raise ValueError("{} has shape {}, expected {}".format(name, tuple(np.shape(value)), shape))
+
+
 class BatchedGaussILRMA:
     def __init__(self, n_basis=10, domain=2, normalize='power', algorithm_spatial='IP', reference_id=0, eps=EPS,
                  threshold=THRESHOLD, device=0):
@@ -48,9 +56,10 @@ class BatchedGaussILRMA:
         """Upload a batch (B,C,F,T) and its initial state; missing state is drawn like the reference's `_reset`
         (np.random.rand: basis (B,N,F,K) first, then activation (B,N,K,T))."""
         B, C, F, T = X.shape
+        K = self.n_basis
+        _check_presets(B, C, F, T, K, demix_filter, basis, activation)
         h = self.open(B, C, F, T)
         h.set_input(X)
-        K = self.n_basis
         if demix_filter is None:
             h.reset_spatial()
         else:
@@ -70,19 +79,24 @@ class BatchedGaussILRMA:
         B, C, F, T = X.shape
         return h.separate((B, C, F, T), dtype, projection_back=True)
 
-    def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline='ramp'):
+    def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline='ramp', device_out=None):
         """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
         `out` (B,N,F,T) complex64 (allocated when None).  The batch is cut into `pipeline` sub-batches (a count, a list of
         sub-batch sizes, or 'ramp' = `ramp_sizes(B)`), each with its own
         handle and CUDA stream and driven by its own host thread, so the host->device copy of one sub-batch and the
         device->host copy of another overlap the update loop of the rest (pass pinned arrays to make the copies
-        asynchronous).  Mixtures are independent, so the result is identical to one undivided call."""
+        asynchronous).  Mixtures are independent, so the result is identical to one undivided call.
+        `device_out`: address of a device buffer (B,N,F,T) complex64 on this model's GPU; the estimates are left there
+        instead of being copied to the host (`separate_batch_sharded` gathers them over NCCL), and None is returned."""
         from concurrent.futures import ThreadPoolExecutor
         B, C, F, T = X.shape
         K = self.n_basis
-        if out is None:
-            out = np.empty((B, C, F, T), dtype=np.complex64)
-        assert out.shape == (B, C, F, T) and out.dtype == np.complex64 and out.flags.c_contiguous
+        _check_presets(B, C, F, T, K, None, basis, activation)
+        if device_out is None:
+            if out is None:
+                out = np.empty((B, C, F, T), dtype=np.complex64)
+            if not (out.shape == (B, C, F, T) and out.dtype == np.complex64 and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous complex64 array of shape {}".format((B, C, F, T)))
         X = X if X.flags.c_contiguous and X.dtype in (np.complex64, np.complex128) else np.ascontiguousarray(X, np.complex128)
         if basis is None:
             basis = np.random.rand(B, C, F, K)
@@ -126,7 +140,11 @@ class BatchedGaussILRMA:
             h.set_state(_lib.STATE_ACTIVATION, activation[lo:hi], np.float64)
             h.set_input_ptr(X[lo:hi].ctypes.data, x_dtype)
             h.run(iteration)
-            h.separate_into(out[lo:hi].ctypes.data, _lib.C64, projection_back=True)
+            if device_out is not None:
+                h.separate_device(int(device_out) + lo * C * F * T * 8, projection_back=True)
+                h.synchronize()
+            else:
+                h.separate_into(out[lo:hi].ctypes.data, _lib.C64, projection_back=True)
             return h.launch_count()
 
         if n_parts == 1:
@@ -134,7 +152,33 @@ class BatchedGaussILRMA:
         else:
             with ThreadPoolExecutor(max_workers=n_parts) as pool:
                 list(pool.map(job, range(n_parts)))
-        return out
+        return out if device_out is None else None
+
+    def separate_batch_sharded(self, X, iteration=100, basis=None, activation=None, group=None, pipeline='ramp', local_only=False):
+        """The multi-GPU whole job (one process per GPU, torch.distributed initialised by the caller): every rank passes the
+        SAME global batch description -- X (B,C,F,T) in host memory, of which it only reads its own contiguous shard
+        `shard_range(B, rank, world)` -- runs its mixtures with `separate_batch` (copies pipelined against the update loop),
+        leaves the estimates on its GPU and takes part in the one collective of the path, the NCCL all-gather of the
+        separated outputs.  Returns a torch tensor (B,N,F,T) complex64 on this rank's GPU holding the estimates of ALL
+        mixtures in batch order (`local_only=True`: only this rank's shard, no collective).  `basis` / `activation` are
+        global (B,...) presets; when None every rank draws its own shard from NumPy's global state."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        B, C, F, T = X.shape
+        lo, hi = shard_range(B, rank, world)
+        _check_presets(B, C, F, T, self.n_basis, None, basis, activation)
+        device = torch.device('cuda', self.device)
+        y_local = torch.empty((hi - lo, C, F, T), dtype=torch.complex64, device=device)
+        if hi > lo:
+            self.separate_batch(X[lo:hi], iteration=iteration, basis=None if basis is None else basis[lo:hi],
+                                activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
+                                device_out=y_local.data_ptr())
+        if local_only or world == 1:
+            return y_local
+        sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
+        return torch.view_as_complex(gather_outputs(torch.view_as_real(y_local), world, group=group, sizes=sizes))
 
     def separate_waveforms(self, x, fft_size, hop_size=None, window_fn='hann', iteration=100, basis=None, activation=None,
                            dtype=np.float64):
@@ -148,8 +192,9 @@ class BatchedGaussILRMA:
             hop_size = fft_size // 2
         window = np.asarray(ss.get_window(window_fn, fft_size), dtype=np.float64)
         F, T = fft_size // 2 + 1, _lib.stft_frames(n_samples, fft_size, hop_size)
-        h = self.open(B, C, F, T)
         K = self.n_basis
+        _check_presets(B, C, F, T, K, None, basis, activation)
+        h = self.open(B, C, F, T)
         h.reset_spatial()
         h.set_state(_lib.STATE_BASIS, np.random.rand(B, C, F, K) if basis is None else basis, np.float64)
         h.set_state(_lib.STATE_ACTIVATION, np.random.rand(B, C, K, T) if activation is None else activation, np.float64)
@@ -200,18 +245,42 @@ def shard_range(n_items, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_outputs(local, world_size, group=None):
-    """All-gather per-rank outputs (torch tensors of equal shape, complex64 viewed as float32 pairs) along the
-    batch axis.  The single collective of the sharded path; runs on NCCL for CUDA tensors, gloo for CPU ones."""
+def gather_outputs(local, world_size, group=None, sizes=None):
+    """All-gather per-rank outputs (torch tensors, complex64 viewed as float32 pairs) along the batch axis, rank order ==
+    batch order.  The single collective of the sharded path; runs on NCCL for CUDA tensors, gloo for CPU ones.
+    `sizes`: per-rank batch sizes when they differ (`shard_range` gives the first ranks one more mixture when the batch is
+    not a multiple of the world size); the shards are then padded to the largest one for the collective and trimmed after.
+    With sizes=None every rank must hold the same number of mixtures (checked)."""
     import torch
     import torch.distributed as dist
     if world_size == 1:
         return local
-    out = torch.empty((world_size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    try:
-        # one collective straight into the final buffer (rank order == batch order)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    except (RuntimeError, NotImplementedError):
-        parts = list(out.chunk(world_size, dim=0))
-        dist.all_gather(parts, local.contiguous(), group=group)
-    return out
+    local = local.contiguous()
+    if sizes is None:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        counts = [torch.empty_like(n) for _ in range(world_size)]
+        dist.all_gather(counts, n, group=group)
+        sizes = [int(c.item()) for c in counts]
+    sizes = [int(v) for v in sizes]
+    if len(sizes) != world_size:
+        raise ValueError("sizes has {} entries for {} ranks".format(len(sizes), world_size))
+    rank = dist.get_rank(group)
+    if sizes[rank] != local.shape[0]:
+        raise ValueError("rank {} holds {} mixtures, sizes says {}".format(rank, local.shape[0], sizes[rank]))
+    tail = tuple(local.shape[1:])
+    if len(set(sizes)) == 1:
+        out = torch.empty((world_size * sizes[0],) + tail, dtype=local.dtype, device=local.device)
+        try:
+            # one collective straight into the final buffer
+            dist.all_gather_into_tensor(out, local, group=group)
+        except (RuntimeError, NotImplementedError):
+            dist.all_gather(list(out.chunk(world_size, dim=0)), local, group=group)
+        return out
+    big = max(sizes)
+    padded = local
+    if local.shape[0] < big:
+        padded = torch.zeros((big,) + tail, dtype=local.dtype, device=local.device)
+        padded[:local.shape[0]] = local
+    parts = [torch.empty((big,) + tail, dtype=local.dtype, device=local.device) for _ in range(world_size)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)

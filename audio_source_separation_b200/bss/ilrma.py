@@ -139,7 +139,7 @@ class ILRMAbase(DeviceModel):
         # device side: handle, input, W (identity unless preset), estimation = separate(X, W)
         cfg = self._config()
         self._open_handle(tuple(sorted(cfg.items())), **cfg)
-        self._send_input(X)
+        self._send_input(X, force=True)
         if not preset_filter:
             self._handle.reset_spatial()
             self._host.pop('demix_filter', None)
@@ -187,8 +187,9 @@ class ILRMAbase(DeviceModel):
         if self.callbacks is None:
             # no callback observes the intermediate states: run the whole loop on the device
             self._push()
-            if self.algorithm_spatial in ['pairwise', 'IP2'] and self.update_pair is not None:
-                self._handle.set_update_pair(*self.update_pair)
+            if self.algorithm_spatial in ['pairwise', 'IP2']:
+                # also when it is None: a reused handle must not continue an earlier run's schedule
+                self._handle.set_update_pair(*(self.update_pair if self.update_pair is not None else (-1, -1)))
             if self.recordable_loss:
                 # the loss after every iteration is reduced on the device and fetched once
                 self.loss.extend(float(v) for v in self._handle.run_record(iteration)[:, 0])
@@ -252,13 +253,15 @@ class ILRMAbase(DeviceModel):
         return _lib.demix(input, demix_filter)
 
     def compute_demix_filter(self, estimation, input):
-        """W = Y X^H (X X^H)^-1 per bin (src/bss/ilrma.py:167-173); served from the device state when the
-        arguments are the model's own estimation / input."""
-        if self._handle is not None and input is self.input:
+        """W = Y X^H (X X^H)^-1 per bin (src/bss/ilrma.py:167-173); served from the device state when the arguments are the model's own
+        estimation / input, from one least-squares kernel over the two arrays otherwise."""
+        own = self._handle is not None and input is self.input and 'estimation' not in self._dirty and (
+            estimation is self._host.get('estimation') or estimation is None)
+        if own and self.algorithm_spatial == 'ISS':
             self._push()
             self._handle.compute_demix_filter()
             return self._handle.get_state(_lib.STATE_DEMIX_FILTER, self._state_shape('demix_filter'), np.complex128)
-        raise NotImplementedError("compute_demix_filter is only available for the model's own state")
+        return np.ascontiguousarray(_lib.least_squares_map(estimation, input).transpose(2, 0, 1))
 
     def compute_negative_loglikelihood(self):
         self._prepare()

@@ -166,6 +166,7 @@ class MultichannelISNMF(MultichannelNMFbase):
         else:
             raise ValueError("Not support")
 
+        self.__dict__['_input_token'] = None   # every __call__ re-reads the mixture, like the reference
         self._prepare()
         self._on_device.update(('basis', 'activation', 'latent', 'spatial', 'estimation'))
         self._device_changed('estimation')
@@ -275,13 +276,9 @@ class MultichannelISNMF(MultichannelNMFbase):
         return float(self._handle.loss()[0])
 
     def separate(self, input):
-        """Multichannel Wiener filter with the current model, image at `reference_id`; `input` must be the mixture the
-        model holds (src/bss/mnmf.py:609-634 is only ever called that way)."""
-        if input is not self.input:
-            if self.input is None or np.shape(input) != np.shape(self.input) or not np.array_equal(input, self.input):
-                raise NotImplementedError("separate() is available for the model's own input")
-        self._prepare()
-        return self._handle.separate((self.n_sources, self.n_bins, self.n_frames), np.complex128, projection_back=False)
+        """Multichannel Wiener filter with the current model, image at `reference_id` (src/bss/mnmf.py:609-634).  `input` may
+        be any mixture of the model's shape: a foreign one is put on the device for this call only."""
+        return _separate_with_model(self, input)
 
 
 class FastMultichannelISNMF(MultichannelNMFbase):
@@ -375,7 +372,7 @@ class FastMultichannelISNMF(MultichannelNMFbase):
             self._snap.pop(name, None)
         cfg = self._config()
         self._open_handle(tuple(sorted(cfg.items())), **cfg)
-        self._send_input(self.input)
+        self._send_input(self.input, force=True)
         self._dirty.discard('diagonalizer')
         self._dirty.discard('spatial_covariance')
         self._handle.reset_spatial()
@@ -445,13 +442,27 @@ class FastMultichannelISNMF(MultichannelNMFbase):
         return float(self._handle.loss()[0])
 
     def separate(self, input):
-        """Multichannel Wiener filter with the current model; `input` must be the mixture the model holds
-        (src/bss/mnmf.py:919-946 is only ever called that way)."""
-        if input is not self.input:
-            if self.input is None or np.shape(input) != np.shape(self.input) or not np.array_equal(input, self.input):
-                raise NotImplementedError("separate() is available for the model's own input")
-        self._prepare()
-        return self._handle.separate((self.n_sources, self.n_bins, self.n_frames), np.complex128, projection_back=False)
+        """Multichannel Wiener filter with the current model (src/bss/mnmf.py:919-946).  `input` may be any mixture of the
+        model's shape: a foreign one is put on the device for this call only."""
+        return _separate_with_model(self, input)
+
+
+def _separate_with_model(model, input):
+    own = model.input
+    if own is None:
+        raise AssertionError("Specify data!")
+    input = np.asarray(input)
+    if input.shape != np.shape(own):
+        raise ValueError("input has shape {}, the model was fitted to {}".format(input.shape, np.shape(own)))
+    model._prepare()
+    shape = (model.n_sources, model.n_bins, model.n_frames)
+    if input is own:
+        return model._handle.separate(shape, np.complex128, projection_back=False)
+    try:
+        model._handle.set_input(input)
+        return model._handle.separate(shape, np.complex128, projection_back=False)
+    finally:
+        model.__dict__['_input_token'] = None   # the model's own mixture goes back up before the next device operation
 
 
 FastMNMF = FastMultichannelISNMF

@@ -180,7 +180,7 @@ void bss_destroy(bss_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->X,   h->Y,    h->W,     h->Wf,    h->basis, h->basis2, h->act,     h->latent, h->U,      h->Cx,
                     h->gate, h->flags, h->pw,   h->scale, h->wfr,   h->wraw,   h->order,   h->logdet, h->aux,    h->G2x,
-                    h->part, h->iw, h->P, h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
+                    h->part, h->iw, h->P, h->eigval, h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
                     h->nz,   h->nt,   h->nv,    h->npart, h->loss_hist, h->G2, h->beff, h->aeff, h->praw,
                     h->sH,   h->sZ,   h->sT,    h->sV,    h->sStat, h->sPart, h->sAcc};
     for (void* p : bufs)
@@ -278,6 +278,10 @@ int bss_reset_spatial(bss_handle* h) {
 
 int bss_set_update_pair(bss_handle* h, int m, int n) {
     if (!h) return BSS_EINVAL;
+    if (m == -1 && n == -1) {   // `update_pair = None`: the next bss_run starts the schedule over at (0, 1)
+        h->pair_m = h->pair_n = -1;
+        return BSS_OK;
+    }
     if (m < 0 || n < 0 || m >= h->N || n >= h->N || m == n) return bss_fail(h, BSS_EINVAL, "invalid update pair");
     h->pair_m = m;
     h->pair_n = n;
@@ -341,7 +345,7 @@ static bool graph_capable(const bss_handle* h) {
 static uint64_t graph_signature(const bss_handle* h) {
     if (h->cfg.method > BSS_AUX_GAUSS_IVA || h->cfg.partitioning) return 0;
     const void* ptrs[] = {h->X, h->Y, h->W, h->Wf, h->basis, h->basis2, h->act, h->U, h->Cx, h->gate, h->flags, h->pw, h->scale,
-                          h->wfr, h->wraw, h->order, h->logdet, h->aux, h->G2x, h->part, h->iw, h->P, h->lossbuf, h->staging};
+                          h->wfr, h->wraw, h->order, h->logdet, h->aux, h->G2x, h->part, h->iw, h->P, h->eigval, h->lossbuf, h->staging};
     uint64_t s = 1469598103934665603ull;
     auto mix = [&](uint64_t v) {
         for (int i = 0; i < 8; ++i) {
@@ -406,6 +410,7 @@ int bss_run(bss_handle* h, int n_iter) {
     const int reps = n_iter / kPerGraph;
     for (int r = 0; r < reps; ++r) BSS_CUDA(h, cudaGraphLaunch(exec, h->stream));
     h->launches += per_graph * reps;
+    h->graph_replays += reps;
     return run_eager(h, n_iter - reps * kPerGraph);
 }
 
@@ -502,6 +507,28 @@ int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int h
     BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
     BSS_TRY(istft_from_device(h, (const cf*)h->staging, h->B * h->N, fft_size, hop_size, window, y, dtype));
     return check_flags(h);
+}
+
+int bss_set_option(bss_handle* h, int option, int value) {
+    if (!h) return BSS_EINVAL;
+    switch (option) {
+        case BSS_OPT_IP_KERNEL:
+            if (value < 0 || value > 3) return bss_fail(h, BSS_EINVAL, "BSS_OPT_IP_KERNEL takes 0 (auto), 1, 2 or 3");
+            if (value != h->opt_ip_kernel) h->graph_sig = 0;   // a kept graph recorded the other kernel
+            h->opt_ip_kernel = value;
+            return BSS_OK;
+    }
+    return bss_fail(h, BSS_EINVAL, "unknown option");
+}
+
+int bss_get_info(bss_handle* h, int what, int64_t* value) {
+    if (!h || !value) return BSS_EINVAL;
+    switch (what) {
+        case BSS_INFO_IP_KERNEL: *value = h->last_ip_kernel; return BSS_OK;
+        case BSS_INFO_GRAPH_REPLAYS: *value = h->graph_replays; return BSS_OK;
+        case BSS_INFO_LAUNCHES: *value = h->launches; return BSS_OK;
+    }
+    return bss_fail(h, BSS_EINVAL, "unknown info");
 }
 
 int bss_compute_demix_filter(bss_handle* h) {

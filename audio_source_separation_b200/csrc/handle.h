@@ -55,6 +55,10 @@ struct bss_handle {
     float* wfr = nullptr;          // [B][N][Tp] AuxIVA frame weights (inverse, floored)
     float* wraw = nullptr;         // [B][N][Tp] AuxIVA frame weights (raw)
     int32_t* order = nullptr;      // [B][F][2] IP2 eigenvalue order
+    double2* eigval = nullptr;     // [B][F][2] IP2 eigenvalues that `order` indexes
+    int opt_ip_kernel = 0;         // BSS_OPT_IP_KERNEL
+    int last_ip_kernel = 0;        // BSS_INFO_IP_KERNEL
+    int64_t graph_replays = 0;     // BSS_INFO_GRAPH_REPLAYS
     double* logdet = nullptr;      // [B][F]
     double* aux = nullptr;         // [B][N] power-normalisation factors of the last update
     double2* G2x = nullptr;        // [B][F][N][C] cross covariance Y X^H / T (ISS filter recovery)
@@ -227,11 +231,14 @@ struct IpArgs {
     int use_gate, floor_den;
     int pair_m, pair_n;   // >= 0: IP2 update of this pair instead of the full sweep
     int32_t* order;       // [B][F][2] IP2 eigenvalue order (may be null)
+    double2* eigval;      // [B][F][2] IP2 eigenvalues (may be null)
+    int variant;          // BSS_OPT_IP_KERNEL: 0 = by problem size, 1 = thread per bin, 2 = lane group per bin
     cf* Wf;               // [B][F][N][C] fp32 mirror of W kept for the streaming kernels (may be null)
 };
 int launch_ip(bss_handle* h, const IpArgs& a);
 int launch_pb_scale(bss_handle* h, const double2* W, const double* Cx, double2* scale, int B, int F, int C, int ref);
 int launch_logdet(bss_handle* h, const double2* W, double* out, long long n_bins, int C, int transpose_sq);
+int launch_lsq_map(bss_handle* h, const double2* A, const double2* Bm, double2* out, int Ra, int Rb, int F, int T);
 int launch_lsq_filter(bss_handle* h, const double2* G, const double* Cx, double2* W, long long n_bins, int C);
 
 struct MuArgs {

@@ -328,7 +328,7 @@ __device__ __forceinline__ void m2_eigvec(const M2& m, cd lam, cd& v0, cd& v1) {
 // Pairwise update of rows m and n.  order_out[0/1] records which of the two closed-form eigenvalues
 // (index 0 = "+" root, 1 = "-" root) went to row m / row n, i.e. argsort(lam)[::-1].
 template <int C>
-__global__ void __launch_bounds__(64) ip2_kernel(const IpArgs a, int32_t* order_out) {
+__global__ void __launch_bounds__(64) ip2_kernel(const IpArgs a, int32_t* order_out, double2* eig_out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)a.B * a.F) return;
     const int b = (int)(idx / a.F), f = (int)(idx - (long long)b * a.F);
@@ -419,8 +419,12 @@ __global__ void __launch_bounds__(64) ip2_kernel(const IpArgs a, int32_t* order_
     const cd det = Mx.a * Mx.d - Mx.b * Mx.c;
     const cd disc = cd_sqrt(tr * tr - 4.0 * det);
     cd lam0 = 0.5 * (tr + disc), lam1 = 0.5 * (tr - disc);
-    // descending complex-lexicographic order (np.argsort(lam)[::-1])
-    const bool first_is_max = (lam0.x > lam1.x) || (lam0.x == lam1.x && lam0.y >= lam1.y);
+    // descending complex-lexicographic order (np.argsort(lam)[::-1]; a tie gives [1, 0], see cd_lex_greater)
+    const bool first_is_max = cd_lex_greater(lam0, lam1);
+    if (eig_out) {
+        eig_out[idx * 2 + 0] = make_double2(lam0.x, lam0.y);
+        eig_out[idx * 2 + 1] = make_double2(lam1.x, lam1.y);
+    }
     const cd lmax = first_is_max ? lam0 : lam1, lmin = first_is_max ? lam1 : lam0;
     if (order_out) {
         order_out[idx * 2 + 0] = first_is_max ? 0 : 1;
@@ -540,17 +544,64 @@ __global__ void __launch_bounds__(64) lsq_filter_kernel(const double2* Gg, const
     store_w<C>(Wg + (size_t)idx * C * C, W);
 }
 
+// M_f = A_f B_f^H (B_f B_f^H)^-1 for arbitrary complex128 arrays A (Ra,F,T), B (Rb,F,T): projection_back(Y, reference)
+// (src/algorithm/projection_back.py:12-21, :25-32) and compute_demix_filter(Y, X) (src/bss/ilrma.py:167-173).
+// One CTA per bin; a warp owns one entry of [A B^H ; B B^H] at a time and sums over the frames in a fixed order.
+template <int RB>
+__global__ void __launch_bounds__(128) lsq_map_kernel(const double2* A, const double2* Bm, double2* out, int Ra, int F, int T,
+                                                      int32_t* flags) {
+    __shared__ cd G[8 + RB][RB];   // rows [0, Ra): A B^H, rows [8, 8 + RB): B B^H
+    const int f = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_entries = (Ra + RB) * RB;
+    for (int e = warp; e < n_entries; e += 4) {
+        const int r = e / RB, n = e - r * RB;
+        const double2* row = r < Ra ? A + ((size_t)r * F + f) * T : Bm + ((size_t)(r - Ra) * F + f) * T;
+        const double2* col = Bm + ((size_t)n * F + f) * T;
+        double sx = 0.0, sy = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            const double2 x = row[t], y = col[t];
+            sx += x.x * y.x + x.y * y.y;   // x conj(y)
+            sy += x.y * y.x - x.x * y.y;
+        }
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        if (lane == 0) G[r < Ra ? r : 8 + (r - Ra)][n] = cd_make(sx, sy);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    Mat<RB> H, Hi;
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) H.a[i][j] = G[8 + i][j];
+    if (!mat_inverse(H, Hi)) atomicAdd(flags, 1);
+    for (int r = 0; r < Ra; ++r)
+#pragma unroll
+        for (int n = 0; n < RB; ++n) {
+            cd s = cd_make(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < RB; ++k) cd_fma(s, G[r][k], Hi.a[k][n]);
+            out[((size_t)r * RB + n) * F + f] = make_double2(s.x, s.y);
+        }
+}
+
 template <int C>
 int launch_ip_t(bss_handle* h, const IpArgs& a, int32_t* order_out) {
     const long long n = (long long)a.B * a.F;
     const int threads = 64;
     const unsigned grid = (unsigned)cdiv(n, threads);
+    // plenty of bins: one thread per bin has no shuffle traffic and wins (171 vs 212 us for 64 x 2049 bins, C = 4);
+    // BSS_OPT_IP_KERNEL overrides the choice (the 8 x 8 thread-per-bin form spills, but it is still the same arithmetic)
+    const bool per_thread = a.variant == 1 || (a.variant != 2 && C <= 4 && n >= 32768);
     if (a.pair_m >= 0) {
-        ip2_kernel<C><<<grid, threads, 0, h->stream>>>(a, order_out);
-    } else if (C <= 4 && n >= 32768) {
-        // plenty of bins: one thread per bin has no shuffle traffic and wins (171 vs 212 us for 64 x 2049 bins, C = 4)
+        ip2_kernel<C><<<grid, threads, 0, h->stream>>>(a, order_out, a.eigval);
+        h->last_ip_kernel = 4;
+    } else if (per_thread) {
         ip_sweep_kernel<C><<<grid, threads, 0, h->stream>>>(a);
+        h->last_ip_kernel = 1;
     } else {
+        h->last_ip_kernel = 2;
         constexpr int G = C <= 2 ? 2 : (C <= 4 ? 4 : 8);
         constexpr int BPW = 32 / G;
         const int warps = 4;
@@ -594,6 +645,23 @@ int launch_pb_scale(bss_handle* h, const double2* W, const double* Cx, double2* 
 int launch_logdet(bss_handle* h, const double2* W, double* out, long long n_bins, int C, int transpose_sq) {
     const unsigned grid = (unsigned)cdiv(n_bins, 64);
     BSS_DISPATCH_C(C, (logdet_kernel<CC_><<<grid, 64, 0, h->stream>>>(W, out, n_bins, transpose_sq)))
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_lsq_map(bss_handle* h, const double2* A, const double2* Bm, double2* out, int Ra, int Rb, int F, int T) {
+    switch (Rb) {
+        case 1: lsq_map_kernel<1><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 2: lsq_map_kernel<2><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 3: lsq_map_kernel<3><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 4: lsq_map_kernel<4><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 5: lsq_map_kernel<5><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 6: lsq_map_kernel<6><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 7: lsq_map_kernel<7><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        case 8: lsq_map_kernel<8><<<F, 128, 0, h->stream>>>(A, Bm, out, Ra, F, T, h->flags); break;
+        default: return bss_fail(h, BSS_EINVAL, "least-squares map: 1 to 8 rows");
+    }
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;

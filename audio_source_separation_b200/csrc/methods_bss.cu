@@ -80,6 +80,8 @@ IpArgs ip_args(bss_handle* h, bool want_power) {
     a.pw = want_power ? h->pw : nullptr;
     a.flags = h->flags;
     a.order = nullptr;
+    a.eigval = nullptr;
+    a.variant = h->opt_ip_kernel == 3 ? 0 : h->opt_ip_kernel;
     a.B = h->B;
     a.F = h->F;
     a.C = h->C;
@@ -174,6 +176,7 @@ int bss_allocate(bss_handle* h) {
     BSS_TRY(dalloc(h, &h->aux, B * N));
     BSS_TRY(dalloc(h, &h->lossbuf, B * F + B));
     BSS_TRY(dalloc(h, &h->order, B * F * 2));
+    BSS_TRY(dalloc(h, &h->eigval, B * F * 2));
     if (uses_model(h)) {
         if (h->cfg.partitioning) {
             BSS_TRY(dalloc(h, &h->basis, B * F * K));
@@ -276,6 +279,7 @@ int ilrma_update_once(bss_handle* h) {
         ip.pair_m = h->pair_m;
         ip.pair_n = h->pair_n;
         ip.order = h->order;
+        ip.eigval = h->eigval;
     }
     BSS_TRY(launch_covariance(h, c));
     BSS_TRY(launch_ip(h, ip));
@@ -324,6 +328,7 @@ int auxiva_update_once(bss_handle* h) {
         ip.pair_m = h->pair_m;
         ip.pair_n = h->pair_n;
         ip.order = h->order;
+        ip.eigval = h->eigval;
     }
     BSS_TRY(launch_covariance(h, c));
     BSS_TRY(launch_ip(h, ip));

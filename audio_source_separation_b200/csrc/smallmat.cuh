@@ -55,6 +55,11 @@ SM_HD void cd_fma(cd& acc, cd a, cd b) {
 // NumPy orders complex numbers lexicographically (real, then imag): `den[den < eps] = eps`
 SM_HD bool cd_less_real(cd a, double e) { return a.x < e || (a.x == e && a.y < 0.0); }
 
+// a > b in NumPy's complex order (real part first, then imaginary).  np.argsort(lam)[::-1] of two eigenvalues puts index 0
+// first exactly when lam[0] > lam[1]: on a tie the ascending (stable for two elements) sort keeps [0, 1] and the reversal
+// gives [1, 0]  (src/bss/ilrma.py:610, src/bss/iva.py:576).
+SM_HD bool cd_lex_greater(cd a, cd b) { return a.x > b.x || (a.x == b.x && a.y > b.y); }
+
 template <int C>
 struct Mat {
     cd a[C][C];

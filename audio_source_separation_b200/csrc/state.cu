@@ -194,6 +194,20 @@ int bss_get_state(bss_handle* h, int which, void* dst, int dtype) {
             BSS_CUDA(h, cudaStreamSynchronize(h->stream));
             return BSS_OK;
         }
+        case BSS_STATE_ORDER: {
+            if (dtype != BSS_I32) return bss_fail(h, BSS_EINVAL, "order is exchanged as int32");
+            if (!h->order || h->cfg.spatial != BSS_SPATIAL_IP2) return bss_fail(h, BSS_EINVAL, "only the pairwise (IP2) update has an eigenvalue order");
+            BSS_CUDA(h, cudaMemcpyAsync(dst, h->order, (size_t)h->B * h->F * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            return BSS_OK;
+        }
+        case BSS_STATE_EIGVAL: {
+            if (dtype != BSS_C128) return bss_fail(h, BSS_EINVAL, "eigenvalues are exchanged as complex128");
+            if (!h->eigval || h->cfg.spatial != BSS_SPATIAL_IP2) return bss_fail(h, BSS_EINVAL, "only the pairwise (IP2) update has eigenvalues");
+            BSS_CUDA(h, cudaMemcpyAsync(dst, h->eigval, (size_t)h->B * h->F * 2 * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            return BSS_OK;
+        }
     }
     return bss_fail(h, BSS_EINVAL, "unknown state");
 }
@@ -307,6 +321,38 @@ int bss_ip_update(int device, int n_channels, int n_bins, void* w, const void* u
     if (rc == BSS_OK) rc = bss_synchronize(h);
     if (rc == BSS_OK) rc = bss_get_state(h, BSS_STATE_DEMIX_FILTER, w, BSS_C128);
     if (rc == BSS_OK && gate) rc = bss_get_state(h, BSS_STATE_GATE, gate, BSS_I32);
+    return done(rc);
+}
+
+int bss_least_squares_map(int device, int n_rows_a, int n_rows_b, int n_bins, int n_frames, const void* a, const void* b,
+                          void* out) {
+    if (!a || !b || !out) return BSS_EINVAL;
+    if (n_rows_a < 1 || n_rows_a > 8 || n_rows_b < 1 || n_rows_b > 8 || n_bins < 1 || n_frames < 1) return BSS_EINVAL;
+    // a throw-away handle only for its stream, error slot and singular-bin flag (two channels, two frames: no big buffers)
+    bss_handle* h = nullptr;
+    int rc = primitive_handle(device, 2, 1, 2, &h);
+    if (rc != BSS_OK) return rc;
+    const size_t na = (size_t)n_rows_a * n_bins * n_frames, nb = (size_t)n_rows_b * n_bins * n_frames;
+    const size_t no = (size_t)n_rows_a * n_rows_b * n_bins;
+    double2 *da = nullptr, *db = nullptr, *dout = nullptr;
+    auto done = [&](int code) {
+        if (da) cudaFree(da);
+        if (db) cudaFree(db);
+        if (dout) cudaFree(dout);
+        bss_destroy(h);
+        return code;
+    };
+    if (cudaMalloc(&da, na * sizeof(double2)) != cudaSuccess || cudaMalloc(&db, nb * sizeof(double2)) != cudaSuccess ||
+        cudaMalloc(&dout, no * sizeof(double2)) != cudaSuccess)
+        return done(BSS_ENOMEM);
+    cudaMemcpyAsync(da, a, na * sizeof(double2), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(db, b, nb * sizeof(double2), cudaMemcpyHostToDevice, h->stream);
+    rc = launch_lsq_map(h, da, db, dout, n_rows_a, n_rows_b, n_bins, n_frames);
+    if (rc == BSS_OK) rc = bss_synchronize(h);
+    if (rc == BSS_OK) {
+        cudaMemcpyAsync(out, dout, no * sizeof(double2), cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = BSS_ECUDA;
+    }
     return done(rc);
 }
 

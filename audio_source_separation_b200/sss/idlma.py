@@ -84,6 +84,7 @@ class IDLMAbase(DeviceModel):
         # W = I for every bin whatever was preset, estimation = separate(X, W) (src/sss/idlma.py:34-36)
         self._host.pop('demix_filter', None)
         self._dirty.discard('demix_filter')
+        self.__dict__['_input_token'] = None   # every __call__ re-reads the mixture, like the reference
         self._prepare()
         self._handle.reset_spatial()
         self._on_device.update(('demix_filter', 'estimation'))

@@ -110,7 +110,26 @@ enum bss_state {
     BSS_STATE_TARGET = 7,
     BSS_STATE_COVARIANCE = 8,
     BSS_STATE_GATE = 9,
-    BSS_STATE_VARIANCE = 10
+    BSS_STATE_VARIANCE = 10,
+    BSS_STATE_ORDER = 11,     /* (F,2) int32    IP2: order = argsort(eigenvalues)[::-1] of the last pairwise update
+                                                (src/bss/ilrma.py:608-611, src/bss/iva.py:574-577) (read only)        */
+    BSS_STATE_EIGVAL = 12     /* (F,2) complex  IP2: the two eigenvalues of V_n^-1 V_m that `order` indexes, in the order the
+                                                device produced them ('+' root, '-' root of the 2x2 characteristic
+                                                polynomial) (read only)                                              */
+};
+
+/* Per-handle switches (bss_set_option) and read-outs (bss_get_info).  Every alternative computes the same update; the
+ * options exist so that tests can force a small problem onto the kernel a large one would take, and so that
+ * measurements can compare them. */
+enum bss_option {
+    BSS_OPT_IP_KERNEL = 0     /* iterative-projection sweep: 0 = choose by problem size (default), 1 = one thread per bin
+                                 (ip_sweep_kernel), 2 = lane group per bin (ip_sweep_group_kernel), 3 = in the epilogue of the
+                                 covariance kernel (no stand-alone launch; Gauss-ILRMA IP with n_channels <= 4 only)       */
+};
+enum bss_info {
+    BSS_INFO_IP_KERNEL = 0,   /* which form the last IP sweep took (values of BSS_OPT_IP_KERNEL; 4 = pairwise ip2_kernel) */
+    BSS_INFO_GRAPH_REPLAYS = 1, /* CUDA-graph replays issued by bss_run / bss_run_record so far */
+    BSS_INFO_LAUNCHES = 2     /* same as bss_launch_count */
 };
 
 typedef struct bss_config {
@@ -165,7 +184,8 @@ int bss_reset_spatial(bss_handle* h);
 
 /* ---- the update loop -------------------------------------------------------------------- */
 /* IP2 pair of the next update (src/bss/ilrma.py:635-646); advanced by the caller exactly as
- * the reference's __call__ does, not by bss_update_once */
+ * the reference's __call__ does, not by bss_update_once.  (-1, -1) clears the pair (`update_pair = None`): the next
+ * bss_run starts the schedule at (0, 1), bss_update_once without a pair fails with BSS_ESTATE. */
 int bss_set_update_pair(bss_handle* h, int m, int n);
 /* Model.update_once(): src/bss/ilrma.py:286 / :814, src/bss/iva.py:469 / :702,
  * src/bss/mnmf.py:737, src/algorithm/nmf.py:182,241,302,329,397,461-595 */
@@ -196,6 +216,9 @@ int bss_separate_device(bss_handle* h, void* y_device, int apply_projection_back
  * estimates; y is (B,N,bss_istft_length(n_frames, fft_size, hop_size)) float32/float64 on the host */
 int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int hop_size, const double* window,
                           int apply_projection_back);
+/* per-handle switches and read-outs, see enum bss_option / enum bss_info */
+int bss_set_option(bss_handle* h, int option, int value);
+int bss_get_info(bss_handle* h, int what, int64_t* value);
 /* ISS keeps no filter: W = Y X^H (X X^H)^-1 (src/bss/ilrma.py:167-173); result is readable as
  * BSS_STATE_DEMIX_FILTER afterwards */
 int bss_compute_demix_filter(bss_handle* h);
@@ -215,6 +238,15 @@ int bss_ip_update(int device, int n_channels, int n_bins, void* w, const void* u
  * plain covariance of x   src/algorithm/projection_back.py:12-21 */
 int bss_projection_back_scale(int device, int n_channels, int n_bins, int n_frames, const void* x,
                               const void* w, int reference_id, void* scale);
+
+/* Per-bin least-squares map  M_f = A_f B_f^H (B_f B_f^H)^-1  for arbitrary arrays:
+ *   projection_back(Y, reference)          src/algorithm/projection_back.py:12-21 (2-D reference: n_rows_a = 1) and :25-32
+ *                                          (3-D reference: n_rows_a = n_channels):  a = reference, b = Y, out = scale
+ *   compute_demix_filter(estimation, input) src/bss/ilrma.py:167-173, src/bss/iva.py:119-125: a = Y, b = X, out[n][c][f] = W[f][n][c]
+ * a (n_rows_a,F,T) complex128, b (n_rows_b,F,T) complex128, out (n_rows_a,n_rows_b,F) complex128; 1 <= rows <= 8.
+ * An exactly singular B_f B_f^H returns BSS_ESINGULAR (np.linalg.inv raises LinAlgError there). */
+int bss_least_squares_map(int device, int n_rows_a, int n_rows_b, int n_bins, int n_frames, const void* a, const void* b,
+                          void* out);
 
 /* Model.separate(input, demix_filter)   src/bss/ilrma.py:153-165, src/bss/iva.py:105-117.
  * x (C,F,T) complex128, w (F,C,C) complex128, y (C,F,T) complex128; `flags` is reserved (0). */

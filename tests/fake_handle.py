@@ -146,7 +146,7 @@ class FakeILRMAHandle:
 
     def set_update_pair(self, m, n):
         self.calls.append(('set_update_pair', m, n))
-        self.pair = (int(m), int(n))
+        self.pair = None if (m, n) == (-1, -1) else (int(m), int(n))
 
     def update_once(self):
         from oracle import ilrma as o_ilrma

@@ -104,6 +104,21 @@ local = torch.from_numpy(full[lo:hi].copy())          # what this rank's GPU wou
 out = gather_outputs(local, world)
 assert out.shape == (B, N, F, T, 2), out.shape
 assert np.array_equal(out.numpy(), full)               # rank order == batch order, bit exact
+# a batch that does not divide by the world size: uneven shards, padded for the collective and trimmed after
+B2 = 7
+full2 = (np.arange(B2 * N * F * T * 2, dtype=np.float32) * 0.5).reshape(B2, N, F, T, 2)
+lo, hi = shard_range(B2, rank, world)
+local2 = torch.from_numpy(full2[lo:hi].copy())
+sizes = [shard_range(B2, r, world)[1] - shard_range(B2, r, world)[0] for r in range(world)]
+assert sizes == [4, 3]
+for given in (sizes, None):
+    out2 = gather_outputs(local2, world, sizes=given)
+    assert out2.shape == (B2, N, F, T, 2) and np.array_equal(out2.numpy(), full2)
+try:
+    gather_outputs(local2, world, sizes=[3, 4])
+    raise SystemExit('a wrong size table must be rejected')
+except ValueError:
+    pass
 dist.barrier()
 dist.destroy_process_group()
 print('ok', rank)
@@ -120,6 +135,18 @@ def test_gather_outputs_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count('ok') == 2
+
+
+def test_batched_presets_are_shape_checked_before_the_library_sees_them():
+    """The C ABI carries no lengths: wrongly shaped presets must raise in Python."""
+    from audio_source_separation_b200.batch import _check_presets
+    B, C, F, T, K = 3, 2, 5, 7, 2
+    _check_presets(B, C, F, T, K, np.zeros((B, F, C, C)), np.zeros((B, C, F, K)), np.zeros((B, C, K, T)))
+    _check_presets(B, C, F, T, K)
+    for bad in (dict(basis=np.zeros((B, C, F, K + 1))), dict(activation=np.zeros((B, C, K, T - 1))),
+                dict(demix_filter=np.zeros((F, C, C))), dict(basis=np.zeros((C, F, K)))):
+        with pytest.raises(ValueError):
+            _check_presets(B, C, F, T, K, **bad)
 
 
 def test_ramp_sizes_cover_the_batch():

@@ -116,3 +116,79 @@ def test_attribute_protocol(ilrma):
     with pytest.raises(ValueError):
         model.basis = np.ones((2, 2))
         model.update_once()
+
+
+def test_refilled_input_buffer_is_uploaded_again(ilrma):
+    """the reference re-reads `self.input` on every call.  A caller that refills the SAME buffer in place
+    (`buf[:] = chunk; model(buf)`) must not be served from the stale device copy, and an in-place refill between two
+    hand-made update_once calls is noticed through the content fingerprint."""
+    mod, fake = ilrma
+    meta, i, o = load_golden('ilrma_ip_power_d2')
+    model = _model(mod, meta, recordable_loss=False)
+    buf = i['X'].copy()
+    model(buf, iteration=1, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    h = fake.instances[-1]
+    assert h.calls.count('set_input') == 1
+    buf[:] = 2.0 * i['X'][::-1]                      # same object, new content
+    out = model(buf, iteration=1, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    assert h.calls.count('set_input') == 2 and rel(h.X, buf) == 0.0
+    want = _model(mod, meta, recordable_loss=False)(buf.copy(), iteration=1, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    assert rel(out, want) < 1e-12
+    # by hand: unchanged buffer -> no upload; refilled buffer -> upload before the update
+    model.update_once()
+    assert h.calls.count('set_input') == 2
+    buf[:] = i['X']
+    model.update_once()
+    assert h.calls.count('set_input') == 3 and rel(h.X, i['X']) == 0.0
+
+
+def test_host_assigned_state_edited_in_place_is_uploaded(ilrma):
+    """a callback that runs before the first device update (iteration 0) reads the host-assigned random / preset
+    basis and may edit it in place; the reference honours that edit, so must we."""
+    mod, fake = ilrma
+    from audio_source_separation_b200 import _lib
+    meta, i, o = load_golden('ilrma_ip_power_d2')
+
+    def first_callback_halves_the_basis(m, state={'done': False}):
+        if not state['done']:
+            state['done'] = True
+            m.basis *= 0.5                            # in place, on the array _reset assigned on the host
+
+    model = _model(mod, meta, recordable_loss=False, callbacks=first_callback_halves_the_basis)
+    out = model(i['X'], iteration=2, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    want = _model(mod, meta, recordable_loss=False)(i['X'], iteration=2, demix_filter=i['W0'], basis=0.5 * i['T0'],
+                                                    activation=i['V0'])
+    assert rel(out, want) < 1e-12
+
+
+def test_recreated_handle_drops_the_stale_estimation_mirror(ilrma):
+    """changing a configuration attribute between update_once calls recreates the handle; the cached host copy
+    of `estimation` must not survive that (it would keep returning the estimates of the old handle)."""
+    mod, fake = ilrma
+    meta, i, o = load_golden('ilrma_ip_power_d2')
+    model = _model(mod, meta, recordable_loss=False)
+    model.input = i['X']
+    model._reset(demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    model.update_once()
+    y1 = model.estimation
+    model.eps = 1e-10                                 # new configuration -> new handle on the next device operation
+    model.update_once()
+    assert len(fake.instances) == 2
+    y2 = model.estimation
+    from oracle import core
+    assert y2 is not y1 and rel(y2, core.demix(i['X'], model.demix_filter)) < 1e-12
+
+
+def test_update_pair_none_restarts_the_device_schedule(ilrma):
+    """`update_pair = None` on a reused handle must reach the device (it maps to (-1, -1))."""
+    mod, fake = ilrma
+    meta, i, o = load_golden('ilrma_ip2_power_d2')
+    model = _model(mod, meta, recordable_loss=False)
+    model(i['X'], iteration=3, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    h = fake.instances[-1]
+    assert h.pair is not None
+    model.update_pair = None
+    out = model(i['X'], iteration=3, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    assert ('set_update_pair', -1, -1) in h.calls
+    fresh = _model(mod, meta, recordable_loss=False)(i['X'], iteration=3, demix_filter=i['W0'], basis=i['T0'], activation=i['V0'])
+    assert rel(out, fresh) < 1e-9
