@@ -26,9 +26,9 @@ F32, F64, C64, C128, I32 = 0, 1, 2, 3, 4
 (STATE_DEMIX_FILTER, STATE_ESTIMATION, STATE_BASIS, STATE_ACTIVATION, STATE_LATENT, STATE_DIAGONALIZER,
  STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE, STATE_VARIANCE, STATE_ORDER, STATE_EIGVAL) = range(13)
 # enum bss_option / bss_info
-OPT_IP_KERNEL = 0
+OPT_IP_KERNEL, OPT_ACT_CHUNKS, OPT_BLOCKING_SYNC = 0, 1, 2
 IP_AUTO, IP_THREAD_PER_BIN, IP_LANE_GROUP, IP_FUSED, IP_PAIRWISE = 0, 1, 2, 3, 4
-INFO_IP_KERNEL, INFO_GRAPH_REPLAYS, INFO_LAUNCHES = 0, 1, 2
+INFO_IP_KERNEL, INFO_GRAPH_REPLAYS, INFO_LAUNCHES, INFO_ACT_CHUNKS = 0, 1, 2, 3
 
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64,
            np.dtype(np.complex128): C128, np.dtype(np.int32): I32}
@@ -195,6 +195,12 @@ class Handle:
         self._check(self._lib.bss_set_input_waveform(self._h, _ptr(x), _DTYPES[x.dtype], x.shape[-1], int(fft_size), int(hop_size),
                                                      _ptr(window)))
 
+    def set_input_waveform_ptr(self, ptr, dtype, n_samples, fft_size, hop_size, window):
+        """Waveforms (B,C,n_samples) already sitting in (pinned) host memory at address `ptr`."""
+        window = as_host(window, np.float64)
+        self._check(self._lib.bss_set_input_waveform(self._h, ctypes.c_void_p(ptr), dtype, int(n_samples), int(fft_size), int(hop_size),
+                                                     _ptr(window)))
+
     def set_input_ptr(self, ptr, dtype):
         """Input already sitting in (pinned) host memory at address `ptr`."""
         self._check(self._lib.bss_set_input(self._h, ctypes.c_void_p(ptr), dtype))
@@ -252,6 +258,11 @@ class Handle:
         self._check(self._lib.bss_separate_waveform(self._h, _ptr(out), _DTYPES[out.dtype], int(fft_size), int(hop_size), _ptr(window),
                                                     1 if projection_back else 0))
         return out
+
+    def separate_waveform_into(self, ptr, dtype, fft_size, hop_size, window, projection_back=True):
+        window = as_host(window, np.float64)
+        self._check(self._lib.bss_separate_waveform(self._h, ctypes.c_void_p(ptr), dtype, int(fft_size), int(hop_size), _ptr(window),
+                                                    1 if projection_back else 0))
 
     def separate_device(self, device_ptr, projection_back=True):
         self._check(self._lib.bss_separate_device(self._h, ctypes.c_void_p(device_ptr), 1 if projection_back else 0))
@@ -353,6 +364,13 @@ def stft_frames(n_samples, fft_size, hop_size):
     n = load().bss_stft_frames(int(n_samples), int(fft_size), int(hop_size))
     if n < 0:
         _raise(n, "invalid STFT geometry")
+    return n
+
+
+def istft_length(n_frames, fft_size, hop_size):
+    n = load().bss_istft_length(int(n_frames), int(fft_size), int(hop_size))
+    if n < 1:
+        _raise(EINVAL, "invalid ISTFT geometry")
     return n
 
 

@@ -79,25 +79,12 @@ class BatchedGaussILRMA:
         B, C, F, T = X.shape
         return h.separate((B, C, F, T), dtype, projection_back=True)
 
-    def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline='ramp', device_out=None):
-        """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
-        `out` (B,N,F,T) complex64 (allocated when None).  The batch is cut into `pipeline` sub-batches (a count, a list of
-        sub-batch sizes, or 'ramp' = `ramp_sizes(B)`), each with its own
-        handle and CUDA stream and driven by its own host thread, so the host->device copy of one sub-batch and the
-        device->host copy of another overlap the update loop of the rest (pass pinned arrays to make the copies
-        asynchronous).  Mixtures are independent, so the result is identical to one undivided call.
-        `device_out`: address of a device buffer (B,N,F,T) complex64 on this model's GPU; the estimates are left there
-        instead of being copied to the host (`separate_batch_sharded` gathers them over NCCL), and None is returned."""
+    def _pipelined(self, B, C, F, T, iteration, basis, activation, pipeline, feed, drain):
+        """Run `feed(h, lo, hi)` -> `iteration` updates -> `drain(h, lo, hi)` for every sub-batch [lo, hi) of a batch of B
+        mixtures, each sub-batch on its own handle, CUDA stream and host thread, so that the copies of one sub-batch overlap
+        the update loop of the others.  `pipeline`: a count, a list of sub-batch sizes, or 'ramp' (`ramp_sizes(B)`)."""
         from concurrent.futures import ThreadPoolExecutor
-        B, C, F, T = X.shape
         K = self.n_basis
-        _check_presets(B, C, F, T, K, None, basis, activation)
-        if device_out is None:
-            if out is None:
-                out = np.empty((B, C, F, T), dtype=np.complex64)
-            if not (out.shape == (B, C, F, T) and out.dtype == np.complex64 and out.flags.c_contiguous):
-                raise ValueError("out must be a C-contiguous complex64 array of shape {}".format((B, C, F, T)))
-        X = X if X.flags.c_contiguous and X.dtype in (np.complex64, np.complex128) else np.ascontiguousarray(X, np.complex128)
         if basis is None:
             basis = np.random.rand(B, C, F, K)
         if activation is None:
@@ -117,8 +104,10 @@ class BatchedGaussILRMA:
             n_parts = max(1, min(int(pipeline), B))
             spans = [shard_range(B, i, n_parts) for i in range(n_parts)]
         if not hasattr(self, '_parts') or len(self._parts) != n_parts:
+            for slot in getattr(self, '_parts', []):
+                if slot is not None:
+                    slot[1].close()
             self._parts = [None] * n_parts
-        x_dtype = _lib.C64 if X.dtype == np.complex64 else _lib.C128
 
         def job(i):
             lo, hi = spans[i]
@@ -132,19 +121,18 @@ class BatchedGaussILRMA:
                                 n_frames=T, n_basis=K, reference_id=self.reference_id, device=self.device,
                                 domain=float(self.domain), eps=float(self.eps), threshold=float(self.threshold),
                                 stream_priority=-(n_parts - 1 - i))   # earlier sub-batches finish first: their D2H overlaps the rest
+                # several host threads per GPU (and several processes per node) wait on their streams at the same time:
+                # sleep instead of spinning, the threads that still have launches to issue need the cores
+                h.set_option(_lib.OPT_BLOCKING_SYNC, 1 if n_parts > 1 else 0)
                 self._parts[i] = slot = (key, h)
             h = slot[1]
             # small uploads first: queued behind the other sub-batches' input copies they would wait for all of them
             h.reset_spatial()
             h.set_state(_lib.STATE_BASIS, basis[lo:hi], np.float64)
             h.set_state(_lib.STATE_ACTIVATION, activation[lo:hi], np.float64)
-            h.set_input_ptr(X[lo:hi].ctypes.data, x_dtype)
+            feed(h, lo, hi)
             h.run(iteration)
-            if device_out is not None:
-                h.separate_device(int(device_out) + lo * C * F * T * 8, projection_back=True)
-                h.synchronize()
-            else:
-                h.separate_into(out[lo:hi].ctypes.data, _lib.C64, projection_back=True)
+            drain(h, lo, hi)
             return h.launch_count()
 
         if n_parts == 1:
@@ -152,7 +140,69 @@ class BatchedGaussILRMA:
         else:
             with ThreadPoolExecutor(max_workers=n_parts) as pool:
                 list(pool.map(job, range(n_parts)))
+
+    def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline='ramp', device_out=None):
+        """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
+        `out` (B,N,F,T) complex64 (allocated when None).  The batch is cut into `pipeline` sub-batches (a count, a list of
+        sub-batch sizes, or 'ramp' = `ramp_sizes(B)`), each with its own
+        handle and CUDA stream and driven by its own host thread, so the host->device copy of one sub-batch and the
+        device->host copy of another overlap the update loop of the rest (pass pinned arrays to make the copies
+        asynchronous).  Mixtures are independent, so the result is identical to one undivided call.
+        `device_out`: address of a device buffer (B,N,F,T) complex64 on this model's GPU; the estimates are left there
+        instead of being copied to the host (`separate_batch_sharded` gathers them over NCCL), and None is returned."""
+        B, C, F, T = X.shape
+        _check_presets(B, C, F, T, self.n_basis, None, basis, activation)
+        if device_out is None:
+            if out is None:
+                out = np.empty((B, C, F, T), dtype=np.complex64)
+            if not (out.shape == (B, C, F, T) and out.dtype == np.complex64 and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous complex64 array of shape {}".format((B, C, F, T)))
+        X = X if X.flags.c_contiguous and X.dtype in (np.complex64, np.complex128) else np.ascontiguousarray(X, np.complex128)
+        x_dtype = _lib.C64 if X.dtype == np.complex64 else _lib.C128
+
+        def feed(h, lo, hi):
+            h.set_input_ptr(X[lo:hi].ctypes.data, x_dtype)
+
+        def drain(h, lo, hi):
+            if device_out is not None:
+                h.separate_device(int(device_out) + lo * C * F * T * 8, projection_back=True)
+                h.synchronize()
+            else:
+                h.separate_into(out[lo:hi].ctypes.data, _lib.C64, projection_back=True)
+
+        self._pipelined(B, C, F, T, iteration, basis, activation, pipeline, feed, drain)
         return out if device_out is None else None
+
+    def separate_waveform_batch(self, x, fft_size, hop_size=None, window_fn='hann', out=None, iteration=100, basis=None,
+                                activation=None, pipeline='ramp'):
+        """The whole job in the time domain, pipelined like `separate_batch`: x (B,C,n_samples) float32/float64 in host
+        memory -> separated signals (B,N,n_out) of the same dtype written to `out` (allocated when None), n_out = the length
+        scipy.signal.istft returns.  STFT (src/transform/stft.py:4-8), update loop, projection back and ISTFT (:10-17) run on
+        the device, so only waveforms cross PCIe: half the bytes of the spectrograms at 50 % overlap."""
+        from scipy import signal as ss
+        if x.dtype not in (np.float32, np.float64) or not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+        B, C, n_samples = x.shape
+        if hop_size is None:
+            hop_size = fft_size // 2
+        window = np.ascontiguousarray(ss.get_window(window_fn, fft_size), dtype=np.float64)
+        F, T = fft_size // 2 + 1, _lib.stft_frames(n_samples, fft_size, hop_size)
+        n_out = _lib.istft_length(T, fft_size, hop_size)
+        _check_presets(B, C, F, T, self.n_basis, None, basis, activation)
+        if out is None:
+            out = np.empty((B, C, n_out), dtype=x.dtype)
+        if not (out.shape == (B, C, n_out) and out.dtype == x.dtype and out.flags.c_contiguous):
+            raise ValueError("out must be a C-contiguous {} array of shape {}".format(x.dtype, (B, C, n_out)))
+        dtype = _lib.F32 if x.dtype == np.float32 else _lib.F64
+
+        def feed(h, lo, hi):
+            h.set_input_waveform_ptr(x[lo:hi].ctypes.data, dtype, n_samples, fft_size, hop_size, window)
+
+        def drain(h, lo, hi):
+            h.separate_waveform_into(out[lo:hi].ctypes.data, dtype, fft_size, hop_size, window, projection_back=True)
+
+        self._pipelined(B, C, F, T, iteration, basis, activation, pipeline, feed, drain)
+        return out
 
     def separate_batch_sharded(self, X, iteration=100, basis=None, activation=None, group=None, pipeline='ramp', local_only=False):
         """The multi-GPU whole job (one process per GPU, torch.distributed initialised by the caller): every rank passes the

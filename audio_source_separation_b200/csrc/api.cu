@@ -70,7 +70,7 @@ int validate(const bss_config* c, std::string* why) {
 int check_flags(bss_handle* h) {
     int32_t flag = 0;
     BSS_CUDA(h, cudaMemcpyAsync(&flag, h->flags, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     if (flag != 0) {
         cudaMemsetAsync(h->flags, 0, sizeof(int32_t), h->stream);
         return bss_fail(h, BSS_ESINGULAR, "Singular matrix");
@@ -168,7 +168,7 @@ int bss_create(const bss_config* cfg, bss_handle** out) {
             rc = bss_allocate(h);
     }
     if (rc != BSS_OK) return fail(rc);
-    CREATE_CUDA(cudaStreamSynchronize(h->stream));
+    CREATE_CUDA(bss_wait(h));
 #undef CREATE_CUDA
     *out = h;
     return BSS_OK;
@@ -177,16 +177,17 @@ int bss_create(const bss_config* cfg, bss_handle** out) {
 void bss_destroy(bss_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) bss_wait(h);
     void* bufs[] = {h->X,   h->Y,    h->W,     h->Wf,    h->basis, h->basis2, h->act,     h->latent, h->U,      h->Cx,
                     h->gate, h->flags, h->pw,   h->scale, h->wfr,   h->wraw,   h->order,   h->logdet, h->aux,    h->G2x,
-                    h->part, h->iw, h->P, h->eigval, h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
+                    h->part, h->iw, h->P, h->eigval, h->scratch2, h->fft_win, h->fft_tw, h->lossbuf, h->staging, h->G, h->target, h->xt, h->mn_acc, h->mn_acc2, h->latent2,
                     h->nz,   h->nt,   h->nv,    h->npart, h->loss_hist, h->G2, h->beff, h->aeff, h->praw,
                     h->sH,   h->sZ,   h->sT,    h->sV,    h->sStat, h->sPart, h->sAcc};
     for (void* p : bufs)
         if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+    if (h->ev_block) cudaEventDestroy(h->ev_block);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -195,7 +196,7 @@ void bss_destroy(bss_handle* h) {
 
 int bss_set_stream(bss_handle* h, void* cuda_stream) {
     if (!h) return BSS_EINVAL;
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return BSS_OK;
 }
@@ -244,26 +245,14 @@ int bss_set_input_waveform(bss_handle* h, const void* x, int dtype, int n_sample
 }
 
 static int finish_input(bss_handle* h) {
-    // plain covariance mean_t x x^H (algebraic power normalisation / projection back)
-    CovArgs ca{};
-    ca.X = h->X;
-    ca.U = h->Cx;
-    ca.B = h->B;
-    ca.F = h->F;
-    ca.C = h->C;
-    ca.NW = 1;
-    ca.T = h->T;
-    ca.Tp = h->Tp;
-    ca.wmode = WM_UNIT;
-    ca.n_sel = 1;
-    ca.wsel[0] = 0;
-    if (h->cfg.method != BSS_IS_MNMF) BSS_TRY(launch_covariance(h, ca));
+    // plain covariance mean_t x x^H (algebraic power normalisation / projection back), accumulated in fp64
+    if (h->cfg.method != BSS_IS_MNMF) BSS_TRY(launch_plain_covariance(h, h->X, h->Cx, h->B, h->F, h->C, h->T, h->Tp));
     h->has_input = true;
     h->y_valid = false;
     // ISS carries estimates instead of a filter: (re)derive them when the filter came first
     if (h->cfg.spatial == BSS_SPATIAL_ISS && h->cfg.method != BSS_FAST_MNMF && h->has_filter) BSS_TRY(bss_refresh_estimates(h));
     // the caller's buffer may be reused as soon as we return
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 
@@ -345,7 +334,7 @@ static bool graph_capable(const bss_handle* h) {
 static uint64_t graph_signature(const bss_handle* h) {
     if (h->cfg.method > BSS_AUX_GAUSS_IVA || h->cfg.partitioning) return 0;
     const void* ptrs[] = {h->X, h->Y, h->W, h->Wf, h->basis, h->basis2, h->act, h->U, h->Cx, h->gate, h->flags, h->pw, h->scale,
-                          h->wfr, h->wraw, h->order, h->logdet, h->aux, h->G2x, h->part, h->iw, h->P, h->eigval, h->lossbuf, h->staging};
+                          h->wfr, h->wraw, h->order, h->logdet, h->aux, h->G2x, h->part, h->iw, h->P, h->eigval, h->scratch2, h->fft_win, h->fft_tw, h->lossbuf, h->staging};
     uint64_t s = 1469598103934665603ull;
     auto mix = [&](uint64_t v) {
         for (int i = 0; i < 8; ++i) {
@@ -517,6 +506,14 @@ int bss_set_option(bss_handle* h, int option, int value) {
             if (value != h->opt_ip_kernel) h->graph_sig = 0;   // a kept graph recorded the other kernel
             h->opt_ip_kernel = value;
             return BSS_OK;
+        case BSS_OPT_BLOCKING_SYNC:
+            h->opt_blocking_sync = value != 0;
+            return BSS_OK;
+        case BSS_OPT_ACT_CHUNKS:
+            if (value < 0) return bss_fail(h, BSS_EINVAL, "BSS_OPT_ACT_CHUNKS takes 0 (auto) or a positive count");
+            if (value != h->opt_act_chunks) h->graph_sig = 0;
+            h->opt_act_chunks = value;
+            return BSS_OK;
     }
     return bss_fail(h, BSS_EINVAL, "unknown option");
 }
@@ -527,6 +524,7 @@ int bss_get_info(bss_handle* h, int what, int64_t* value) {
         case BSS_INFO_IP_KERNEL: *value = h->last_ip_kernel; return BSS_OK;
         case BSS_INFO_GRAPH_REPLAYS: *value = h->graph_replays; return BSS_OK;
         case BSS_INFO_LAUNCHES: *value = h->launches; return BSS_OK;
+        case BSS_INFO_ACT_CHUNKS: *value = h->last_act_chunks; return BSS_OK;
     }
     return bss_fail(h, BSS_EINVAL, "unknown info");
 }

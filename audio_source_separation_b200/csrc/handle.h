@@ -56,6 +56,10 @@ struct bss_handle {
     float* wraw = nullptr;         // [B][N][Tp] AuxIVA frame weights (raw)
     int32_t* order = nullptr;      // [B][F][2] IP2 eigenvalue order
     double2* eigval = nullptr;     // [B][F][2] IP2 eigenvalues that `order` indexes
+    int opt_blocking_sync = 0;     // BSS_OPT_BLOCKING_SYNC
+    cudaEvent_t ev_block = nullptr;
+    int opt_act_chunks = 0;        // BSS_OPT_ACT_CHUNKS
+    int last_act_chunks = 0;       // BSS_INFO_ACT_CHUNKS
     int opt_ip_kernel = 0;         // BSS_OPT_IP_KERNEL
     int last_ip_kernel = 0;        // BSS_INFO_IP_KERNEL
     int64_t graph_replays = 0;     // BSS_INFO_GRAPH_REPLAYS
@@ -69,6 +73,13 @@ struct bss_handle {
     double* lossbuf = nullptr;     // [B][F] per-bin loss terms + [B] results
     void* staging = nullptr;       // device staging for host <-> device layout conversion
     size_t staging_bytes = 0;
+    void* scratch2 = nullptr;      // second device scratch (ISTFT frames + time-domain output of the waveform path)
+    size_t scratch2_bytes = 0;
+    float* fft_win = nullptr;      // cached STFT tables of the waveform path: window, twiddles (kernels_stft.cu)
+    float2* fft_tw = nullptr;
+    int fft_N = 0;
+    double fft_win_sum = 0.0;
+    std::vector<double> fft_window_host;
     void* pinned = nullptr;        // pinned host bounce buffer
     size_t pinned_bytes = 0;
 
@@ -103,6 +114,20 @@ struct bss_handle {
     size_t loss_hist_elems = 0;
 };
 
+// Wait for the handle's stream.  Default: cudaStreamSynchronize (the driver spins, lowest latency).  With
+// BSS_OPT_BLOCKING_SYNC the thread sleeps on a blocking event instead: a pipelined whole-job call runs several host threads
+// per GPU and several processes per node, and that many spinning waiters starve the threads that still have launches to issue.
+static inline cudaError_t bss_wait(bss_handle* h) {
+    if (!h->opt_blocking_sync) return cudaStreamSynchronize(h->stream);
+    if (!h->ev_block) {
+        cudaError_t e = cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(h->ev_block, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(h->ev_block);
+}
+
 #define BSS_CUDA(h, call)                                                                              \
     do {                                                                                               \
         cudaError_t e__ = (call);                                                                      \
@@ -130,6 +155,16 @@ static inline int ensure_staging(bss_handle* h, size_t bytes) {
     h->staging_bytes = 0;
     BSS_CUDA(h, cudaMalloc(&h->staging, bytes));
     h->staging_bytes = bytes;
+    return BSS_OK;
+}
+
+static inline int ensure_scratch2(bss_handle* h, size_t bytes) {
+    if (bytes <= h->scratch2_bytes) return BSS_OK;
+    if (h->scratch2) cudaFree(h->scratch2);
+    h->scratch2 = nullptr;
+    h->scratch2_bytes = 0;
+    BSS_CUDA(h, cudaMalloc(&h->scratch2, bytes));
+    h->scratch2_bytes = bytes;
     return BSS_OK;
 }
 
@@ -218,6 +253,7 @@ struct CovArgs {
     int n_sel;
 };
 int launch_covariance(bss_handle* h, const CovArgs& a);
+int launch_plain_covariance(bss_handle* h, const cf* X, double* Cx, int B, int F, int C, int T, int Tp);   // fp64 accumulation
 
 struct IpArgs {
     double2* W;           // [B][F][N][C]
@@ -265,6 +301,7 @@ int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, cons
 int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const double2* scale, int B, int N, int C, int F, int K,
                         double domain);
 int launch_sync_wf(bss_handle* h, const double2* W, cf* Wf, long long n);
+int launch_identity_filter(bss_handle* h, double2* W, cf* Wf, long long n_bins, int N, int C);
 int launch_widen(bss_handle* h, const cf* in, double2* out, long long n);
 int launch_separate(bss_handle* h, const cf* X, const cf* Wf, const double2* scale, cf* Y, cf* out, int B, int C, int F, int T,
                     int Tp);

@@ -122,6 +122,16 @@ __global__ void __launch_bounds__(256) sync_wf_kernel(const double2* W, cf* Wf, 
     if (i < n) Wf[i] = cf_make((float)W[i].x, (float)W[i].y);
 }
 
+// W = I for every bin (src/bss/ilrma.py:67-69), both precisions, without a host round trip
+__global__ void __launch_bounds__(256) identity_filter_kernel(double2* W, cf* Wf, long long n, int N, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int rc = (int)(i % ((long long)N * C));
+    const double v = (rc / C) == (rc % C) ? 1.0 : 0.0;
+    W[i] = make_double2(v, 0.0);
+    Wf[i] = cf_make((float)v, 0.f);
+}
+
 // ------------------------------------------------------------------------------------------- demixing
 struct SepParams {
     const cf* X;
@@ -416,6 +426,14 @@ int launch_widen(bss_handle* h, const cf* in, double2* out, long long n) {
 
 int launch_sync_wf(bss_handle* h, const double2* W, cf* Wf, long long n) {
     sync_wf_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(W, Wf, n);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
+int launch_identity_filter(bss_handle* h, double2* W, cf* Wf, long long n_bins, int N, int C) {
+    const long long n = n_bins * N * C;
+    identity_filter_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(W, Wf, n, N, C);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;

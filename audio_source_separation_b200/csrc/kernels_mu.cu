@@ -719,6 +719,7 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
             best = c;
         }
     }
+    if (h->opt_act_chunks > 0) best = std::min(h->opt_act_chunks, a.F);   // BSS_OPT_ACT_CHUNKS: reproduce another batch's order
     p.bins_per_chunk = (int)cdiv(a.F, best);
     p.n_chunks = (int)cdiv(a.F, p.bins_per_chunk);
     const long long n_items = per_chunk * p.n_chunks;
@@ -745,6 +746,7 @@ int launch_mu_act_stream(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     if (n_chunks_out) *n_chunks_out = p.n_chunks;
+    h->last_act_chunks = p.n_chunks;
     *done = true;
     return BSS_OK;
 }
@@ -773,9 +775,11 @@ int launch_mu_act_t(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_ou
     long long per_chunk_items = (long long)a.B * n_slabs * n_kc;
     int n_chunks = (int)cdiv(want, per_chunk_items);
     if (n_chunks < 1) n_chunks = 1;
+    if (h->opt_act_chunks > 0) n_chunks = std::min(h->opt_act_chunks, a.F);
     int bins_per_chunk = (int)cdiv(a.F, n_chunks);
-    if (bins_per_chunk < 4) bins_per_chunk = a.F < 4 ? a.F : 4;
+    if (bins_per_chunk < 4 && h->opt_act_chunks <= 0) bins_per_chunk = a.F < 4 ? a.F : 4;
     n_chunks = (int)cdiv(a.F, bins_per_chunk);
+    h->last_act_chunks = n_chunks;
     const size_t need = (size_t)a.B * n_chunks * C * a.K * 2 * a.Tp;
     if (need > h->part_elems) {
         if (h->part) cudaFree(h->part);

@@ -8,6 +8,8 @@
 // shared memory (twiddles from a table rounded from float64) with the usual split/merge step.  The forward
 // kernel can write straight into a handle's block-interleaved bin tiles, so a mixture is fed to the update
 // loop from its waveform without the (twice larger) spectrogram ever crossing PCIe.
+#include <cstring>
+
 #include "handle.h"
 
 namespace {
@@ -317,24 +319,80 @@ int bss_istft(int device, int n_signals, int n_frames, int fft_size, int hop_siz
 
 }  // extern "C"
 
-// waveform feed of a handle: x (B, C, n_samples) on the host -> h->X tiles, no spectrogram on the host
+// STFT tables of a handle: built once per (fft_size, window) and kept, so that the waveform feed of a job-after-job handle
+// allocates nothing (cudaMalloc / cudaFree synchronise the whole device and would serialise the pipelined sub-batches)
+static int handle_tables(bss_handle* h, const double* window, int N, FftTables* t) {
+    if (h->fft_N != N || h->fft_window_host.size() != (size_t)N || memcmp(h->fft_window_host.data(), window, N * sizeof(double)) != 0) {
+        FftTables fresh;
+        const int rc = make_tables(window, N, h->stream, &fresh);
+        if (rc != BSS_OK) {
+            free_tables(&fresh);
+            return rc;
+        }
+        if (h->fft_win) cudaFree(h->fft_win);
+        if (h->fft_tw) cudaFree(h->fft_tw);
+        h->fft_win = fresh.win;
+        h->fft_tw = fresh.tw;
+        h->fft_win_sum = fresh.win_sum;
+        h->fft_N = N;
+        h->fft_window_host.assign(window, window + N);
+    }
+    t->win = h->fft_win;
+    t->tw = h->fft_tw;
+    t->win_sum = h->fft_win_sum;
+    return BSS_OK;
+}
+
+// waveform feed of a handle: x (B, C, n_samples) on the host -> h->X tiles, no spectrogram on the host.  Everything is queued
+// on the handle's stream; the caller (finish_input) waits before the host buffer is handed back.
 int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int fft_size, int hop_size, const double* window) {
     if (!pow2(fft_size) || fft_size < 8 || fft_size > 16384) return bss_fail(h, BSS_EUNSUPPORTED, "fft_size must be a power of two in [8, 16384]");
     if (dtype != BSS_F32 && dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "waveforms are float32 or float64");
     if (fft_size / 2 + 1 != h->F) return bss_fail(h, BSS_EINVAL, "n_bins of the handle must be fft_size / 2 + 1");
     const int n_frames = bss_stft_frames(n_samples, fft_size, hop_size);
     if (n_frames != h->T) return bss_fail(h, BSS_EINVAL, "n_frames of the handle does not match the waveform length");
+    FftTables t;
+    if (handle_tables(h, window, fft_size, &t) != BSS_OK) return bss_fail(h, BSS_ENOMEM, "stft tables");
+    const int S = h->B * h->C;
+    const long long n = (long long)S * n_samples;
+    // staging: [float waveform | double waveform (float64 input only)]
+    BSS_TRY(ensure_staging(h, (size_t)n * sizeof(float) + (dtype == BSS_F64 ? (size_t)n * sizeof(double) : 0)));
+    float* xf = (float*)h->staging;
+    if (dtype == BSS_F32) {
+        BSS_CUDA(h, cudaMemcpyAsync(xf, x, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        double* staged = (double*)((char*)h->staging + (size_t)n * sizeof(float));
+        BSS_CUDA(h, cudaMemcpyAsync(staged, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        to_float_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(staged, xf, n);
+        h->launches += 1;
+    }
     // pad frames (T odd) must read as zero
-    BSS_CUDA(h, cudaMemsetAsync(h->X, 0, (size_t)h->B * h->F * h->C * h->Tp * sizeof(cf), h->stream));
-    const int rc = stft_common(h->cfg.device, h->stream, h->B * h->C, n_samples, fft_size, hop_size, window, x, dtype, nullptr, h->X, h->C,
-                               h->Tp, n_frames);
-    if (rc != BSS_OK) return bss_fail(h, rc, "stft failed");
+    if (h->Tp != h->T) BSS_CUDA(h, cudaMemsetAsync(h->X, 0, (size_t)h->B * h->F * h->C * h->Tp * sizeof(cf), h->stream));
+    StftParams p{};
+    p.x = xf;
+    p.win = t.win;
+    p.tw = t.tw;
+    p.S = S;
+    p.n_samples = n_samples;
+    p.N = fft_size;
+    p.hop = hop_size;
+    p.n_frames = n_frames;
+    p.scale = (float)(1.0 / t.win_sum);
+    p.out128 = nullptr;
+    p.X = h->X;
+    p.C = h->C;
+    p.Tp = h->Tp;
+    const size_t smem = (size_t)fft_size * sizeof(float2);
+    BSS_CUDA(h, cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_frames, S);
+    stft_kernel<<<grid, fft_threads(fft_size), smem, h->stream>>>(p);
     h->launches += 1;
+    BSS_CUDA(h, cudaGetLastError());
     return BSS_OK;
 }
 
 // time-domain output of a handle: ISTFT of the separated estimates already sitting on the device as (B, N, F, T) complex64;
-// y (B, N, out_len) float32/float64 on the host
+// y (B, N, out_len) float32/float64 on the host.  Scratch lives on the handle (no allocation per call).
 int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, int hop_size, const double* window, void* y, int dtype) {
     if (!pow2(fft_size) || fft_size < 8 || fft_size > 16384) return bss_fail(h, BSS_EUNSUPPORTED, "fft_size must be a power of two in [8, 16384]");
     if (dtype != BSS_F32 && dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "waveforms are float32 or float64");
@@ -343,44 +401,36 @@ int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, i
     const int out_len = bss_istft_length(n_frames, fft_size, hop_size);
     if (out_len < 1) return bss_fail(h, BSS_EINVAL, "invalid ISTFT geometry");
     FftTables t;
-    int rc = make_tables(window, fft_size, h->stream, &t);
-    float* frames = nullptr;
-    void* od = nullptr;
+    if (handle_tables(h, window, fft_size, &t) != BSS_OK) return bss_fail(h, BSS_ENOMEM, "stft tables");
     const size_t esz = dtype == BSS_F32 ? 4 : 8;
-    if (rc == BSS_OK && (cudaMalloc(&frames, (size_t)n_signals * n_frames * fft_size * sizeof(float)) != cudaSuccess ||
-                         cudaMalloc(&od, (size_t)n_signals * out_len * esz) != cudaSuccess))
-        rc = BSS_ENOMEM;
-    if (rc == BSS_OK) {
-        IstftParams<float2> p{};
-        p.z = z;
-        p.win = t.win;
-        p.tw = t.tw;
-        p.S = n_signals;
-        p.N = fft_size;
-        p.hop = hop_size;
-        p.n_frames = n_frames;
-        p.scale = (float)(t.win_sum / (double)(fft_size / 2));
-        p.frames = frames;
-        const size_t smem = (size_t)fft_size * sizeof(float2);
-        cudaFuncSetAttribute(istft_frames_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid(n_frames, n_signals);
-        istft_frames_kernel<float2><<<grid, fft_threads(fft_size), smem, h->stream>>>(p);
-        const long long n = (long long)n_signals * out_len;
-        if (dtype == BSS_F32)
-            istft_ola_kernel<float><<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(frames, t.win, (float*)od, n_signals, fft_size, hop_size,
-                                                                                  n_frames, out_len);
-        else
-            istft_ola_kernel<double><<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(frames, t.win, (double*)od, n_signals, fft_size,
-                                                                                   hop_size, n_frames, out_len);
-        h->launches += 2;
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(y, od, (size_t)n * esz, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = BSS_ECUDA;
-    }
-    if (frames) cudaFree(frames);
-    if (od) cudaFree(od);
-    free_tables(&t);
-    if (rc != BSS_OK) return bss_fail(h, rc, "istft failed");
+    const size_t frames_bytes = ((size_t)n_signals * n_frames * fft_size * sizeof(float) + 255) / 256 * 256;
+    BSS_TRY(ensure_scratch2(h, frames_bytes + (size_t)n_signals * out_len * esz));
+    float* frames = (float*)h->scratch2;
+    void* od = (char*)h->scratch2 + frames_bytes;
+    IstftParams<float2> p{};
+    p.z = z;
+    p.win = t.win;
+    p.tw = t.tw;
+    p.S = n_signals;
+    p.N = fft_size;
+    p.hop = hop_size;
+    p.n_frames = n_frames;
+    p.scale = (float)(t.win_sum / (double)(fft_size / 2));
+    p.frames = frames;
+    const size_t smem = (size_t)fft_size * sizeof(float2);
+    BSS_CUDA(h, cudaFuncSetAttribute(istft_frames_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_frames, n_signals);
+    istft_frames_kernel<float2><<<grid, fft_threads(fft_size), smem, h->stream>>>(p);
+    const long long n = (long long)n_signals * out_len;
+    if (dtype == BSS_F32)
+        istft_ola_kernel<float><<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(frames, t.win, (float*)od, n_signals, fft_size, hop_size,
+                                                                              n_frames, out_len);
+    else
+        istft_ola_kernel<double><<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(frames, t.win, (double*)od, n_signals, fft_size,
+                                                                               hop_size, n_frames, out_len);
+    h->launches += 2;
+    BSS_CUDA(h, cudaGetLastError());
+    BSS_CUDA(h, cudaMemcpyAsync(y, od, (size_t)n * esz, cudaMemcpyDeviceToHost, h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }

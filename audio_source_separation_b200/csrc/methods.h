@@ -27,6 +27,7 @@ int mnmf_reset(bss_handle* h);
 int mnmf_update_once(bss_handle* h);
 int mnmf_loss(bss_handle* h);
 int mnmf_separate(bss_handle* h, cf* out);
+int mnmf_covariance_only(bss_handle* h);
 
 // Sawada IS-MNMF: methods_smnmf.cu
 int smnmf_allocate(bss_handle* h);

@@ -207,16 +207,7 @@ int bss_allocate(bss_handle* h) {
 
 // W = I for every bin (src/bss/ilrma.py:67-69); for ISS the estimates start as Y = X
 int bss_reset_filter(bss_handle* h) {
-    const size_t n = (size_t)h->B * h->F * h->N * h->C;
-    BSS_TRY(ensure_pinned(h, n * sizeof(double2)));
-    double2* w = (double2*)h->pinned;
-    for (size_t i = 0; i < n; ++i) {
-        const size_t rc = i % ((size_t)h->N * h->C);
-        w[i] = make_double2((rc / h->C) == (rc % h->C) ? 1.0 : 0.0, 0.0);
-    }
-    BSS_CUDA(h, cudaMemcpyAsync(h->W, w, n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-    BSS_TRY(launch_sync_wf(h, h->W, h->Wf, (long long)n));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_TRY(launch_identity_filter(h, h->W, h->Wf, (long long)h->B * h->F, h->N, h->C));
     h->has_filter = true;
     h->pair_m = h->pair_n = -1;
     if (is_iss(h) && h->has_input) BSS_TRY(bss_refresh_estimates(h));
@@ -239,6 +230,7 @@ int bss_filter_from_estimates(bss_handle* h) {
 }
 
 int bss_covariance_only(bss_handle* h) {
+    if (h->cfg.method == BSS_FAST_MNMF) return mnmf_covariance_only(h);
     CovArgs c = cov_args(h);
     if (h->cfg.method == BSS_GAUSS_ILRMA && h->cfg.partitioning) {
         BSS_TRY(launch_part_expand(h));
@@ -344,7 +336,7 @@ int idlma_set_variance(bss_handle* h, const double* r) {
     BSS_TRY(ensure_staging(h, n * sizeof(double)));
     BSS_CUDA(h, cudaMemcpyAsync(h->staging, r, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     BSS_TRY(launch_import_variance(h, (const double*)h->staging, h->iw, h->B, h->N, h->F, h->T, h->Tp, h->cfg.eps));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));   // the host buffer is borrowed for this call only
+    BSS_CUDA(h, bss_wait(h));   // the host buffer is borrowed for this call only
     h->has_variance = true;
     return BSS_OK;
 }

@@ -56,7 +56,7 @@ int mnmf_reset(bss_handle* h) {
     BSS_CUDA(h, cudaMemcpyAsync(h->W, q, nq * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     BSS_CUDA(h, cudaMemcpyAsync(h->G, g, ng * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     BSS_TRY(launch_sync_wf(h, h->W, h->Wf, (long long)nq));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     h->has_filter = true;
     return BSS_OK;
 }
@@ -121,6 +121,30 @@ int mnmf_loss(bss_handle* h) {
     BSS_TRY(launch_mnmf_xt(h));
     BSS_TRY(launch_mnmf_loss_terms(h));
     return launch_loss_finish(h, h->lossbuf, h->logdet, (double)h->T, h->B, h->F, result);
+}
+
+// the covariance-accumulate step of update_diagonalizer alone (bss_time_covariance): inverse weights from (W, H, g), then
+// all M weighted covariances of every bin
+int mnmf_covariance_only(bss_handle* h) {
+    BSS_TRY(launch_mnmf_weights(h, 1));
+    bool on_tensor_cores = false;
+    BSS_TRY(launch_covariance_mma(h, h->X, h->iw, h->U, h->B, h->F, h->C, h->C, h->T, h->Tp, &on_tensor_cores));
+    if (on_tensor_cores) return BSS_OK;
+    BSS_TRY(launch_mnmf_weights(h, 0));
+    CovArgs c{};
+    c.X = h->X;
+    c.U = h->U;
+    c.B = h->B;
+    c.F = h->F;
+    c.C = h->C;
+    c.NW = h->C;
+    c.T = h->T;
+    c.Tp = h->Tp;
+    c.wmode = WM_EXPLICIT;
+    c.iw = h->iw;
+    c.n_sel = h->C;
+    for (int i = 0; i < 8; ++i) c.wsel[i] = i;
+    return launch_covariance(h, c);
 }
 
 int mnmf_separate(bss_handle* h, cf* out) { return launch_mnmf_separate(h, out); }

@@ -16,12 +16,12 @@ int dalloc(bss_handle* h, T** p, size_t n) {
 
 int put(bss_handle* h, double* dev, const void* src, size_t n) {
     BSS_CUDA(h, cudaMemcpyAsync(dev, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 int get(bss_handle* h, const double* dev, void* dst, size_t n) {
     BSS_CUDA(h, cudaMemcpyAsync(dst, dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 

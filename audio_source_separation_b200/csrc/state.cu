@@ -20,7 +20,7 @@ int put_rows(bss_handle* h, float* dev, const double* src, size_t rows, int T, i
         for (int t = T; t < Tp; ++t) p[r * Tp + t] = 0.f;
     }
     BSS_CUDA(h, cudaMemcpyAsync(dev, p, rows * Tp * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 
@@ -29,7 +29,7 @@ int get_rows(bss_handle* h, const float* dev, double* dst, size_t rows, int T, i
     BSS_TRY(ensure_pinned(h, rows * Tp * sizeof(float)));
     float* p = (float*)h->pinned;
     BSS_CUDA(h, cudaMemcpyAsync(p, dev, rows * Tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     for (size_t r = 0; r < rows; ++r)
         for (int t = 0; t < T; ++t) dst[r * T + t] = (double)p[r * Tp + t];
     return BSS_OK;
@@ -39,13 +39,13 @@ int get_rows(bss_handle* h, const float* dev, double* dst, size_t rows, int T, i
 int put_f64(bss_handle* h, double* dev, const void* src, size_t n) {
     if (!dev) return bss_fail(h, BSS_EINVAL, "this model has no such state");
     BSS_CUDA(h, cudaMemcpyAsync(dev, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 int get_f64(bss_handle* h, const double* dev, void* dst, size_t n) {
     if (!dev) return bss_fail(h, BSS_EINVAL, "this model has no such state");
     BSS_CUDA(h, cudaMemcpyAsync(dst, dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+    BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 
@@ -86,7 +86,7 @@ int bss_set_state(bss_handle* h, int which, const void* src, int dtype) {
             const size_t n = (size_t)h->B * h->F * h->C * h->C;
             BSS_CUDA(h, cudaMemcpyAsync(h->W, src, n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
             BSS_TRY(launch_sync_wf(h, h->W, h->Wf, (long long)n));
-            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            BSS_CUDA(h, bss_wait(h));
             h->has_filter = true;
             h->y_valid = false;
             if (h->cfg.spatial == BSS_SPATIAL_ISS && h->cfg.method != BSS_FAST_MNMF && h->has_input)
@@ -138,7 +138,7 @@ int bss_get_state(bss_handle* h, int which, void* dst, int dtype) {
             if (!h->W) return bss_fail(h, BSS_EINVAL, "this model has no demixing filter");
             const size_t n = (size_t)h->B * h->F * h->C * h->C;
             BSS_CUDA(h, cudaMemcpyAsync(dst, h->W, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            BSS_CUDA(h, bss_wait(h));
             return BSS_OK;
         }
         case BSS_STATE_ESTIMATION: return bss_separate(h, dst, dtype, 0);
@@ -165,7 +165,7 @@ int bss_get_state(bss_handle* h, int which, void* dst, int dtype) {
             BSS_TRY(ensure_pinned(h, n_mat * CC * sizeof(double)));
             double* p = (double*)h->pinned;
             BSS_CUDA(h, cudaMemcpyAsync(p, h->U, n_mat * CC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            BSS_CUDA(h, bss_wait(h));
             double* out = (double*)dst;
             for (size_t m = 0; m < n_mat; ++m) {
                 const double* q = p + m * CC;
@@ -191,21 +191,21 @@ int bss_get_state(bss_handle* h, int which, void* dst, int dtype) {
             if (!h->gate) return bss_fail(h, BSS_EINVAL, "this model has no gate");
             const size_t n = (size_t)h->B * h->C * h->F;
             BSS_CUDA(h, cudaMemcpyAsync(dst, h->gate, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            BSS_CUDA(h, bss_wait(h));
             return BSS_OK;
         }
         case BSS_STATE_ORDER: {
             if (dtype != BSS_I32) return bss_fail(h, BSS_EINVAL, "order is exchanged as int32");
             if (!h->order || h->cfg.spatial != BSS_SPATIAL_IP2) return bss_fail(h, BSS_EINVAL, "only the pairwise (IP2) update has an eigenvalue order");
             BSS_CUDA(h, cudaMemcpyAsync(dst, h->order, (size_t)h->B * h->F * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            BSS_CUDA(h, bss_wait(h));
             return BSS_OK;
         }
         case BSS_STATE_EIGVAL: {
             if (dtype != BSS_C128) return bss_fail(h, BSS_EINVAL, "eigenvalues are exchanged as complex128");
             if (!h->eigval || h->cfg.spatial != BSS_SPATIAL_IP2) return bss_fail(h, BSS_EINVAL, "only the pairwise (IP2) update has eigenvalues");
             BSS_CUDA(h, cudaMemcpyAsync(dst, h->eigval, (size_t)h->B * h->F * 2 * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-            BSS_CUDA(h, cudaStreamSynchronize(h->stream));
+            BSS_CUDA(h, bss_wait(h));
             return BSS_OK;
         }
     }
@@ -351,7 +351,7 @@ int bss_least_squares_map(int device, int n_rows_a, int n_rows_b, int n_bins, in
     if (rc == BSS_OK) rc = bss_synchronize(h);
     if (rc == BSS_OK) {
         cudaMemcpyAsync(out, dout, no * sizeof(double2), cudaMemcpyDeviceToHost, h->stream);
-        if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = BSS_ECUDA;
+        if (bss_wait(h) != cudaSuccess) rc = BSS_ECUDA;
     }
     return done(rc);
 }
@@ -386,7 +386,7 @@ int bss_projection_back_scale(int device, int n_channels, int n_bins, int n_fram
     if (rc == BSS_OK) rc = bss_synchronize(h);
     if (rc == BSS_OK) {
         cudaMemcpyAsync(scale, h->scale, (size_t)n_channels * n_bins * sizeof(double2), cudaMemcpyDeviceToHost, h->stream);
-        cudaStreamSynchronize(h->stream);
+        bss_wait(h);
     }
     return done(rc);
 }

@@ -61,6 +61,7 @@ def update_pairwise(st, kind, eps=EPS, threshold=THRESHOLD):
     U_m = weighted_covariance(st['X'], r_m)
     U_n = weighted_covariance(st['X'], r_n)
     info = ip2_pair(st['W'], U_m, U_n, m, n, threshold)
+    st['ip2_info'] = info   # (order, gate_m, gate_n, eigenvalues) of this update, for the index-parity tests
     st['Y'] = demix(st['X'], st['W'])
     return info
 

@@ -123,7 +123,8 @@ def ip2_pair(W, U_m, U_n, m, n, threshold=THRESHOLD):
     """Pairwise (IP2) update of rows m and n, W modified in place.
 
     src/bss/ilrma.py:599-626, src/bss/iva.py:566-592.
-    Returns (order (F,2) int, gate_m (F,), gate_n (F,)) for index-parity tests.
+    Returns (order (F,2) int, gate_m (F,), gate_n (F,), lam (F,2) complex) for index-parity tests: `order` indexes
+    `lam`, the eigenvalues in the order LAPACK returned them.
     """
     n_bins, n_ch = W.shape[0], W.shape[2]
     E = np.zeros((n_bins, n_ch, 2))
@@ -148,7 +149,7 @@ def ip2_pair(W, U_m, U_n, m, n, threshold=THRESHOLD):
     w_n = (G_n @ v_n[..., np.newaxis]).squeeze(axis=-1).conj()
     W[:, m, :] = np.where(ok_m[:, np.newaxis], w_m, W[:, m, :])
     W[:, n, :] = np.where(ok_n[:, np.newaxis], w_n, W[:, n, :])
-    return order, ok_m, ok_n
+    return order, ok_m, ok_n, lam
 
 
 def iss_sweep(Y, R):

@@ -127,6 +127,7 @@ def spatial_model_ip(st, domain=2, partitioning=False, eps=EPS, threshold=THRESH
     R[R < eps] = eps
     U = weighted_covariance(st['X'], R)
     gate = ip_rows(st['W'], U, threshold)
+    st['ip_gate'] = gate   # (N,F) condition-gate decisions of this update, for the index-parity tests
     st['Y'] = demix(st['X'], st['W'])
     return U, gate
 
@@ -148,6 +149,7 @@ def spatial_model_pairwise(st, domain=2, partitioning=False, eps=EPS, threshold=
     U_m = weighted_covariance(st['X'], R_m)
     U_n = weighted_covariance(st['X'], R_n)
     info = ip2_pair(st['W'], U_m, U_n, m, n, threshold)
+    st['ip2_info'] = info   # (order, gate_m, gate_n, eigenvalues) of this update, for the index-parity tests
     st['Y'] = demix(st['X'], st['W'])
     return info
 

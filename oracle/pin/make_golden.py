@@ -8,6 +8,7 @@ has no /root/reference: tests only ever read the committed .npz files.
 
     python oracle/pin/make_golden.py            # regenerate everything
     python oracle/pin/make_golden.py idlma      # only the GaussIDLMA fixtures
+    python oracle/pin/make_golden.py audio      # only the real-recording fixtures (dataset/sample-song of the reference)
 """
 import json
 import os
@@ -334,12 +335,77 @@ def case_seeded_dropin():
          {'X': X}, want)
 
 
+# ------------------------------------------------------------------------------- real recordings
+
+AUDIO_BIN_STEP = 8   # the fixtures keep every 8th bin of the (2, 2049, 209) output in full and the per-bin norms of all bins
+
+
+def audio_mixture(name='sample-2_mixture_16000'):
+    """The reference notebooks' own preparation of the sample recording (egs/bss-example/ilrma/*.ipynb cells 14-19):
+    scipy.io.wavfile -> / 32768 -> scipy.signal.stft(nperseg=4096, noverlap=2048)."""
+    from scipy.io import wavfile
+    sr, data = wavfile.read('/root/reference/dataset/sample-song/{}.wav'.format(name))
+    assert data.dtype == np.int16 and data.ndim == 2
+    return sr, np.ascontiguousarray(data.T)            # (n_channels, n_samples) int16
+
+
+def audio_stft(pcm, fft_size=4096, hop_size=2048):
+    from scipy import signal as ss
+    x = pcm.astype(np.float64) / 32768
+    _, _, X = ss.stft(x, nperseg=fft_size, noverlap=fft_size - hop_size)
+    return X
+
+
+def audio_outputs(out, demix_filter, loss, extra=None):
+    want = {'output_bins': out[:, ::AUDIO_BIN_STEP].astype(np.complex64), 'output_bin_norms': np.linalg.norm(out, axis=2),
+            'output_abs_sum': np.float64(np.abs(out).sum()), 'demix_filter': demix_filter, 'loss': np.array(loss)}
+    want.update(extra or {})
+    return want
+
+
+def case_audio(sample='sample-2_mixture_16000', iters=100):
+    """100 iterations on a real two-channel recording: cond_2(W U) reaches 1e8 (AuxLaplaceIVA) and 3e11 (GaussILRMA, K = 5),
+    784 of the 2049 bins start above 1e6 -- the inputs that stress the fp64 per-bin solve and the condition gate."""
+    sr, pcm = audio_mixture(sample)
+    X = audio_stft(pcm)
+    tag = sample.split('_')[0].replace('-', '')       # sample2
+    pcm_file = 'audio_{}_pcm'.format(tag)
+    np.savez_compressed(os.path.join(GOLDEN, pcm_file + '.npz'), pcm=pcm, sr=np.int64(sr))   # shared by the cases below
+    # AuxLaplaceIVA-IP, default constructor
+    model = AuxLaplaceIVA()
+    out = model(X, iteration=iters)
+    o_out, st, o_loss = auxiva.run(X, iteration=iters, kind='laplace')
+    check('audio auxiva', {'output': o_out, 'demix_filter': st['W'], 'loss': np.array(o_loss)},
+          {'output': out, 'demix_filter': model.demix_filter, 'loss': np.array(model.loss)}, 1e-7)
+    save('audio_{}_auxiva_laplace_ip'.format(tag),
+         dict(model='AuxLaplaceIVA', algorithm_spatial='IP', iteration=iters, sample=sample, sr=int(sr), fft_size=4096, hop_size=2048,
+              bin_step=AUDIO_BIN_STEP, pcm_file=pcm_file),
+         {}, audio_outputs(out, model.demix_filter, model.loss))
+    # GaussILRMA K = 5, seeded like the reference's own __main__ (src/bss/ilrma.py:1271)
+    np.random.seed(111)
+    model = GaussILRMA(n_basis=5)
+    out = model(X, iteration=iters)
+    np.random.seed(111)
+    o_out, st, o_loss = ilrma.run(X, iteration=iters, n_basis=5)
+    check('audio ilrma', {'output': o_out, 'demix_filter': st['W'], 'basis': st['T'], 'activation': st['V'], 'loss': np.array(o_loss)},
+          {'output': out, 'demix_filter': model.demix_filter, 'basis': model.basis, 'activation': model.activation,
+           'loss': np.array(model.loss)}, 1e-6)
+    save('audio_{}_ilrma_k5'.format(tag),
+         dict(model='GaussILRMA', n_basis=5, domain=2, partitioning=False, normalize='power', algorithm_spatial='IP', iteration=iters,
+              seed=111, sample=sample, sr=int(sr), fft_size=4096, hop_size=2048, bin_step=AUDIO_BIN_STEP,
+              pcm_file=pcm_file),
+         {}, audio_outputs(out, model.demix_filter, model.loss, {'basis': model.basis, 'activation': model.activation}))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     print("pinning oracle against /root/reference (numpy {}), tol {:g}".format(np.__version__, TOL))
     if sys.argv[1:] == ['idlma']:    # regenerate just these fixtures
         case_idlma('idlma_gauss_d2', 3, 17, 40, 2, 3)
         case_idlma('idlma_gauss_d1', 2, 17, 40, 1, 3)
+        return
+    if sys.argv[1:] == ['audio']:
+        case_audio()
         return
     case_primitives()
     case_seeded_dropin()
@@ -376,6 +442,7 @@ def main():
     case_nmf('nmf_t', 't', 33, 24, 4, 5, nu=50.0)
     for alg in ('naive-multipricative', 'mm', 'me', 'mm_fast'):
         case_nmf('nmf_cauchy_' + alg.replace('-', '_'), 'cauchy', 33, 24, 4, 5, algorithm=alg)
+    case_audio()
     print("all oracle functions pinned against the reference.")
 
 

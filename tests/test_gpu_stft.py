@@ -110,3 +110,26 @@ def test_waveform_in_waveform_out(cuda_device):
         want = ss.istft(Y, nperseg=fft, noverlap=fft - hop, window='hann')[1]
         assert y[b].shape == want.shape
         assert rel(y[b], want) < 1e-3
+
+
+def test_pipelined_waveform_job_equals_the_single_handle_call(cuda_device):
+    """BatchedGaussILRMA.separate_waveform_batch (sub-batches on their own handles / streams / host threads, float32 and
+    float64 waveforms, scratch kept on the handles from job to job) against separate_waveforms on one handle."""
+    from audio_source_separation_b200.batch import BatchedGaussILRMA
+    rng = np.random.default_rng(5)
+    B, C, K, n_samples, fft, hop = 6, 3, 2, 5000, 256, 128
+    x = rng.standard_normal((B, C, n_samples))
+    F = fft // 2 + 1
+    T = len(ss.stft(x[0, 0], nperseg=fft, noverlap=fft - hop)[1])
+    T0, V0 = rng.random((B, C, F, K)), rng.random((B, C, K, T))
+    want = BatchedGaussILRMA(n_basis=K).separate_waveforms(x, fft, hop, iteration=12, basis=T0, activation=V0)
+    model = BatchedGaussILRMA(n_basis=K)
+    for pipeline in (1, 3, [1, 4, 1]):
+        for job in range(2):   # the second job reuses handles, cached FFT tables, scratch buffers and the captured graph
+            got = model.separate_waveform_batch(x, fft, hop, iteration=12, basis=T0, activation=V0, pipeline=pipeline)
+            assert got.shape == want.shape and got.dtype == np.float64
+            assert rel(got, want) < 1e-5
+    got32 = model.separate_waveform_batch(x.astype(np.float32), fft, hop, iteration=12, basis=T0, activation=V0, pipeline=2)
+    assert got32.dtype == np.float32 and rel(got32, want) < 1e-4
+    with pytest.raises(ValueError):
+        model.separate_waveform_batch(x, fft, hop, iteration=1, basis=T0[:, :, :-1], activation=V0)

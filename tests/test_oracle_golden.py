@@ -173,3 +173,29 @@ def test_every_fixture_is_checked_on_both_sides():
 
     assert [n for n in names if not used(n, cpu_src)] == []
     assert [n for n in names if not used(n, gpu_src)] == []
+
+
+@pytest.mark.parametrize('name', ['audio_sample2_auxiva_laplace_ip', 'audio_sample2_ilrma_k5'])
+def test_oracle_reproduces_the_reference_on_the_sample_recording(name):
+    """100 iterations on the reference's own sample recording (cond_2 up to 3.4e11): the fixtures hold what the unmodified
+    reference produced (oracle/pin/make_golden.py audio); the oracle must land on the same trajectory."""
+    import os
+    from scipy import signal as ss
+    from conftest import GOLDEN
+    meta, _, o = load_golden(name)
+    assert meta['pcm_file'] == 'audio_sample2_pcm'    # the int16 samples of dataset/sample-song/sample-2_mixture_16000.wav
+    z = np.load(os.path.join(GOLDEN, meta['pcm_file'] + '.npz'))
+    x = z['pcm'].astype(np.float64) / 32768
+    _, _, X = ss.stft(x, nperseg=meta['fft_size'], noverlap=meta['fft_size'] - meta['hop_size'])
+    assert X.shape == (2, 2049, 209)
+    if meta['model'] == 'AuxLaplaceIVA':
+        from oracle import auxiva
+        out, st, loss = auxiva.run(X, iteration=meta['iteration'], kind='laplace')
+    else:
+        from oracle import ilrma
+        np.random.seed(meta['seed'])
+        out, st, loss = ilrma.run(X, iteration=meta['iteration'], n_basis=meta['n_basis'])
+        assert rel(st['T'], o['basis']) < 1e-6 and rel(st['V'], o['activation']) < 1e-6
+    assert rel(out[:, ::meta['bin_step']], o['output_bins']) < 1e-6       # the fixture stores these bins as complex64
+    assert rel(np.linalg.norm(out, axis=2), o['output_bin_norms']) < 1e-6
+    assert rel(st['W'], o['demix_filter']) < 1e-6 and rel(loss, o['loss']) < 1e-9
