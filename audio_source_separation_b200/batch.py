@@ -109,6 +109,11 @@ class BatchedGaussILRMA:
                     slot[1].close()
             self._parts = [None] * n_parts
 
+        import time
+        t_start = time.perf_counter()
+        marks = [dict(size=hi - lo) for lo, hi in spans]
+        self.timeline = marks   # per sub-batch: ms since the start of the call at which each phase returned to the host
+
         def job(i):
             lo, hi = spans[i]
             key = (hi - lo, C, F, T)
@@ -130,9 +135,13 @@ class BatchedGaussILRMA:
             h.reset_spatial()
             h.set_state(_lib.STATE_BASIS, basis[lo:hi], np.float64)
             h.set_state(_lib.STATE_ACTIVATION, activation[lo:hi], np.float64)
+            marks[i]['state'] = round(1e3 * (time.perf_counter() - t_start), 2)
             feed(h, lo, hi)
+            marks[i]['input'] = round(1e3 * (time.perf_counter() - t_start), 2)
             h.run(iteration)
+            marks[i]['queued'] = round(1e3 * (time.perf_counter() - t_start), 2)
             drain(h, lo, hi)
+            marks[i]['out'] = round(1e3 * (time.perf_counter() - t_start), 2)
             return h.launch_count()
 
         if n_parts == 1:
