@@ -627,6 +627,7 @@ def run_gpu_arm(args):
                                                                              activation=V0, pipeline=pipeline))
     if not np.all(np.isfinite(w_out[0, :, ::997])):
         raise RuntimeError("non-finite separated waveform")
+    timelines = {"spectrogram": getattr(model, 'timeline', None), "waveform": getattr(wave_model, 'timeline', None)}
     del wave_model
 
     # ---- the sharded product call and its one collective --------------------------------------------
@@ -672,6 +673,10 @@ def run_gpu_arm(args):
         del y_dev
 
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get('BENCH_TIMELINE'):   # per-rank phase marks of the last end-to-end jobs (diagnostics)
+        with open('{}.rank{}.json'.format(os.environ['BENCH_TIMELINE'], rank), 'w') as fh:
+            json.dump({"rank": rank, "world": world, "spectrogram_s": spec_s, "waveform_s": wave_s, "timelines": timelines,
+                       "cpus": len(os.sched_getaffinity(0))}, fh)
 
     if rank == 0:
         cpu, cfgs = None, None

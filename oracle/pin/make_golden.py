@@ -371,8 +371,20 @@ def case_audio(sample='sample-2_mixture_16000', iters=100):
     tag = sample.split('_')[0].replace('-', '')       # sample2
     pcm_file = 'audio_{}_pcm'.format(tag)
     np.savez_compressed(os.path.join(GOLDEN, pcm_file + '.npz'), pcm=pcm, sr=np.int64(sr))   # shared by the cases below
+    half = iters // 2
+    snap = {}
+
+    def snapshot(m, count=[0]):
+        # callbacks run after _reset (call 0) and after every iteration: keep the state half way, before the few
+        # ill-conditioned bins whose trajectories are sensitive to single-precision storage have had time to drift
+        if count[0] == half:
+            snap['demix_filter_half'] = m.demix_filter.copy()
+            if hasattr(m, 'basis'):
+                snap['basis_half'], snap['activation_half'] = m.basis.copy(), m.activation.copy()
+        count[0] += 1
+
     # AuxLaplaceIVA-IP, default constructor
-    model = AuxLaplaceIVA()
+    model = AuxLaplaceIVA(callbacks=snapshot)
     out = model(X, iteration=iters)
     o_out, st, o_loss = auxiva.run(X, iteration=iters, kind='laplace')
     check('audio auxiva', {'output': o_out, 'demix_filter': st['W'], 'loss': np.array(o_loss)},
@@ -380,10 +392,17 @@ def case_audio(sample='sample-2_mixture_16000', iters=100):
     save('audio_{}_auxiva_laplace_ip'.format(tag),
          dict(model='AuxLaplaceIVA', algorithm_spatial='IP', iteration=iters, sample=sample, sr=int(sr), fft_size=4096, hop_size=2048,
               bin_step=AUDIO_BIN_STEP, pcm_file=pcm_file),
-         {}, audio_outputs(out, model.demix_filter, model.loss))
+         {}, audio_outputs(out, model.demix_filter, model.loss, dict(snap, half=np.int64(half))))
     # GaussILRMA K = 5, seeded like the reference's own __main__ (src/bss/ilrma.py:1271)
     np.random.seed(111)
-    model = GaussILRMA(n_basis=5)
+    snap = {}
+
+    def snapshot2(m, count=[0]):
+        if count[0] == half:
+            snap['demix_filter_half'], snap['basis_half'], snap['activation_half'] = m.demix_filter.copy(), m.basis.copy(), m.activation.copy()
+        count[0] += 1
+
+    model = GaussILRMA(n_basis=5, callbacks=snapshot2)
     out = model(X, iteration=iters)
     np.random.seed(111)
     o_out, st, o_loss = ilrma.run(X, iteration=iters, n_basis=5)
@@ -394,7 +413,7 @@ def case_audio(sample='sample-2_mixture_16000', iters=100):
          dict(model='GaussILRMA', n_basis=5, domain=2, partitioning=False, normalize='power', algorithm_spatial='IP', iteration=iters,
               seed=111, sample=sample, sr=int(sr), fft_size=4096, hop_size=2048, bin_step=AUDIO_BIN_STEP,
               pcm_file=pcm_file),
-         {}, audio_outputs(out, model.demix_filter, model.loss, {'basis': model.basis, 'activation': model.activation}))
+         {}, audio_outputs(out, model.demix_filter, model.loss, dict(snap, half=np.int64(half), basis=model.basis, activation=model.activation)))
 
 
 def main():

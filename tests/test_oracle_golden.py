@@ -188,14 +188,20 @@ def test_oracle_reproduces_the_reference_on_the_sample_recording(name):
     x = z['pcm'].astype(np.float64) / 32768
     _, _, X = ss.stft(x, nperseg=meta['fft_size'], noverlap=meta['fft_size'] - meta['hop_size'])
     assert X.shape == (2, 2049, 209)
+    half = int(o['half'])
     if meta['model'] == 'AuxLaplaceIVA':
         from oracle import auxiva
+        _, st_half, _ = auxiva.run(X, iteration=half, kind='laplace', record_loss=False)
         out, st, loss = auxiva.run(X, iteration=meta['iteration'], kind='laplace')
     else:
         from oracle import ilrma
         np.random.seed(meta['seed'])
+        _, st_half, _ = ilrma.run(X, iteration=half, n_basis=meta['n_basis'], record_loss=False)
+        assert rel(st_half['T'], o['basis_half']) < 1e-7 and rel(st_half['V'], o['activation_half']) < 1e-7
+        np.random.seed(meta['seed'])
         out, st, loss = ilrma.run(X, iteration=meta['iteration'], n_basis=meta['n_basis'])
         assert rel(st['T'], o['basis']) < 1e-6 and rel(st['V'], o['activation']) < 1e-6
+    assert rel(st_half['W'], o['demix_filter_half']) < 1e-7
     assert rel(out[:, ::meta['bin_step']], o['output_bins']) < 1e-6       # the fixture stores these bins as complex64
     assert rel(np.linalg.norm(out, axis=2), o['output_bin_norms']) < 1e-6
     assert rel(st['W'], o['demix_filter']) < 1e-6 and rel(loss, o['loss']) < 1e-9
