@@ -506,6 +506,11 @@ int bss_set_option(bss_handle* h, int option, int value) {
             if (value != h->opt_ip_kernel) h->graph_sig = 0;   // a kept graph recorded the other kernel
             h->opt_ip_kernel = value;
             return BSS_OK;
+        case BSS_OPT_SOURCE_MODEL:
+            if (value < 0 || value > 2) return bss_fail(h, BSS_EINVAL, "BSS_OPT_SOURCE_MODEL takes 0 (auto), 1 or 2");
+            if (value != h->opt_source_model) h->graph_sig = 0;
+            h->opt_source_model = value;
+            return BSS_OK;
         case BSS_OPT_BLOCKING_SYNC:
             h->opt_blocking_sync = value != 0;
             return BSS_OK;
@@ -525,6 +530,7 @@ int bss_get_info(bss_handle* h, int what, int64_t* value) {
         case BSS_INFO_GRAPH_REPLAYS: *value = h->graph_replays; return BSS_OK;
         case BSS_INFO_LAUNCHES: *value = h->launches; return BSS_OK;
         case BSS_INFO_ACT_CHUNKS: *value = h->last_act_chunks; return BSS_OK;
+        case BSS_INFO_SOURCE_MODEL: *value = h->last_source_model; return BSS_OK;
     }
     return bss_fail(h, BSS_EINVAL, "unknown info");
 }

@@ -56,6 +56,8 @@ struct bss_handle {
     float* wraw = nullptr;         // [B][N][Tp] AuxIVA frame weights (raw)
     int32_t* order = nullptr;      // [B][F][2] IP2 eigenvalue order
     double2* eigval = nullptr;     // [B][F][2] IP2 eigenvalues that `order` indexes
+    int opt_source_model = 0;      // BSS_OPT_SOURCE_MODEL
+    int last_source_model = 0;     // BSS_INFO_SOURCE_MODEL
     int opt_blocking_sync = 0;     // BSS_OPT_BLOCKING_SYNC
     cudaEvent_t ev_block = nullptr;
     int opt_act_chunks = 0;        // BSS_OPT_ACT_CHUNKS
@@ -296,6 +298,8 @@ struct MuArgs {
 };
 int launch_mu_basis(bss_handle* h, const MuArgs& a);
 int launch_mu_act(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_out = nullptr);
+int launch_mu_act_finish(bss_handle* h, const MuArgs& a, float* act, int n_chunks);
+int launch_mu_fused(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done);   // kernels_mu_fused.cu
 int launch_normalize_power(bss_handle* h, double2* W, cf* Wf, float* basis, const double* pw, int B, int N, int C, int F, int K,
                            double domain, double eps, double* aux_out);
 int launch_normalize_pb(bss_handle* h, double2* W, cf* Wf, float* basis, const double2* scale, int B, int N, int C, int F, int K,

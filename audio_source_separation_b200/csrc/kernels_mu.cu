@@ -838,6 +838,15 @@ int launch_mu_basis(bss_handle* h, const MuArgs& a) {
     return rc;
 }
 
+// second stage alone: the partial sums of `n_chunks` bin chunks already sit in h->part (launch_mu_fused)
+int launch_mu_act_finish(bss_handle* h, const MuArgs& a, float* act, int n_chunks) {
+    const long long blocks = (long long)a.B * a.C * a.K * ((a.Tp + 31) / 32);
+    mu_act_finish_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(a, h->part, act, a.C, n_chunks);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
 int launch_mu_act(bss_handle* h, const MuArgs& a, float* act, int* n_chunks_out) {
     int rc = BSS_OK;
     const bool from_y = a.Y != nullptr;

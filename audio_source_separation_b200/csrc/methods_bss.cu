@@ -115,6 +115,23 @@ int source_model(bss_handle* h, int sel_m, int sel_n) {
     MuArgs m = mu_args(h);
     m.sel_m = sel_m;
     m.sel_n = sel_n;
+    // one pass over X for both factor updates where the fused kernel covers the configuration (kernels_mu_fused.cu);
+    // BSS_OPT_SOURCE_MODEL = 1 keeps the three-pass form (basis kernel -> power tiles -> activation kernel)
+    if (h->opt_source_model != 1 && !is_iss(h)) {
+        bool fused = false;
+        int n_chunks = 0;
+        BSS_TRY(launch_mu_fused(h, m, &n_chunks, &fused));
+        if (fused) {
+            float* t = h->basis;
+            h->basis = h->basis2;
+            h->basis2 = t;
+            m.basis = h->basis;
+            m.basis_out = h->basis2;
+            h->last_source_model = 2;
+            return launch_mu_act_finish(h, m, h->act, n_chunks);
+        }
+    }
+    h->last_source_model = 1;
     const bool handoff = power_handoff(h);
     if (handoff) m.Pout = h->P;
     BSS_TRY(launch_mu_basis(h, m));

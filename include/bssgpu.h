@@ -125,6 +125,9 @@ enum bss_option {
     BSS_OPT_IP_KERNEL = 0,    /* iterative-projection sweep: 0 = choose by problem size (default), 1 = one thread per bin
                                  (ip_sweep_kernel), 2 = lane group per bin (ip_sweep_group_kernel), 3 = in the epilogue of the
                                  covariance kernel (no stand-alone launch; Gauss-ILRMA IP with n_channels <= 4 only)       */
+    BSS_OPT_SOURCE_MODEL = 3, /* NMF source model of (t-)ILRMA: 0 = fused single-pass kernel where it covers the configuration
+                                 (Gauss, domain 2, n_basis 2, 4 channels, n_frames <= 512), else three passes (default);
+                                 1 = always three passes (basis kernel, power tiles, activation kernel); 2 = same as 0      */
     BSS_OPT_BLOCKING_SYNC = 2,/* 1: host waits of this handle sleep on a blocking CUDA event instead of spinning in
                                  cudaStreamSynchronize (for many host threads / processes per node); 0 = spin (default) */
     BSS_OPT_ACT_CHUNKS = 1    /* number of bin chunks of the cross-bin (activation) reduction of the source model; 0 = chosen
@@ -135,7 +138,8 @@ enum bss_info {
     BSS_INFO_IP_KERNEL = 0,   /* which form the last IP sweep took (values of BSS_OPT_IP_KERNEL; 4 = pairwise ip2_kernel) */
     BSS_INFO_GRAPH_REPLAYS = 1, /* CUDA-graph replays issued by bss_run / bss_run_record so far */
     BSS_INFO_LAUNCHES = 2,    /* same as bss_launch_count */
-    BSS_INFO_ACT_CHUNKS = 3   /* bin chunks the last activation update used (see BSS_OPT_ACT_CHUNKS) */
+    BSS_INFO_ACT_CHUNKS = 3,  /* bin chunks the last activation update used (see BSS_OPT_ACT_CHUNKS) */
+    BSS_INFO_SOURCE_MODEL = 4 /* form the last source-model update took: 1 = three passes, 2 = fused single pass */
 };
 
 typedef struct bss_config {

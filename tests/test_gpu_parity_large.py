@@ -317,3 +317,41 @@ def test_projection_back_reference_signature(cuda_device):
     assert rel(model.compute_demix_filter(Yr, X), core.estimate_demix_filter(Yr, X)) < 1e-9
     with pytest.raises(np.linalg.LinAlgError):
         projection_back(np.zeros_like(Yr), ref)
+
+
+@pytest.mark.parametrize('F,T', [(40, 131), (17, 512), (9, 385), (5, 2), (33, 48), (150, 200)])
+def test_fused_source_model_against_oracle_and_three_pass(cuda_device, F, T):
+    """The single-pass source-model kernel (kernels_mu_fused.cu: basis and activation update from one stream over X) on
+    whole-block, ragged and odd frame counts: against the oracle (src/bss/ilrma.py:413-428) and against the three-pass form
+    (BSS_OPT_SOURCE_MODEL = 1), which differs only in the order of the partial sums."""
+    from audio_source_separation_b200 import _lib
+    C, K, B = 4, 2, 3
+    X = np.stack([synth.mix2(C, F, T, seed=40 + b) for b in range(B)])
+    rng = np.random.default_rng(11)
+    T0 = rng.random((B, C, F, K)).astype(np.float32).astype(np.float64)
+    V0 = rng.random((B, C, K, T)).astype(np.float32).astype(np.float64)
+    W0 = np.stack([synth.random_demix(C, F, seed=b) for b in range(B)])
+    results = {}
+    for mode in (_lib.SOURCE_MODEL_FUSED, _lib.SOURCE_MODEL_THREE_PASS):
+        h = _ilrma_handle(_lib, B, C, F, T, K)
+        h.set_option(_lib.OPT_SOURCE_MODEL, mode)
+        h.set_input(X)
+        h.set_state(_lib.STATE_DEMIX_FILTER, W0, np.complex128)
+        h.set_state(_lib.STATE_BASIS, T0, np.float64)
+        h.set_state(_lib.STATE_ACTIVATION, V0, np.float64)
+        h.update_once()
+        assert h.get_info(_lib.INFO_SOURCE_MODEL) == mode
+        first = _state(_lib, h, B, C, F, T, K)
+        h.run(12)      # graph replay of the fused form included
+        results[mode] = (first, _state(_lib, h, B, C, F, T, K))
+        h.close()
+    fused, three = results[_lib.SOURCE_MODEL_FUSED], results[_lib.SOURCE_MODEL_THREE_PASS]
+    for b in range(B):
+        st = o_ilrma.init_state(X[b], K, W=W0[b], T=T0[b], V=V0[b])
+        o_ilrma.update_once(st)
+        for got, want in zip(fused[0], (st['W'], st['T'], st['V'])):
+            assert rel(got[b], want) < 2e-4
+    for x, y in zip(fused[0], three[0]):
+        assert rel(x, y) < 2e-5
+    for x, y in zip(fused[1], three[1]):
+        assert rel(x, y) < 5e-4
