@@ -72,6 +72,7 @@ SIGNATURES = {
     'bss_separate': (_i, [_vp, _vp, _i, _i]),
     'bss_separate_device': (_i, [_vp, _vp, _i]),
     'bss_separate_waveform': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    'bss_separate_waveform_device': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     'bss_compute_demix_filter': (_i, [_vp]),
     'bss_set_option': (_i, [_vp, _i, _i]),
     'bss_get_info': (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
@@ -264,6 +265,11 @@ class Handle:
         window = as_host(window, np.float64)
         self._check(self._lib.bss_separate_waveform(self._h, ctypes.c_void_p(ptr), dtype, int(fft_size), int(hop_size), _ptr(window),
                                                     1 if projection_back else 0))
+
+    def separate_waveform_device(self, device_ptr, dtype, fft_size, hop_size, window, projection_back=True):
+        window = as_host(window, np.float64)
+        self._check(self._lib.bss_separate_waveform_device(self._h, ctypes.c_void_p(device_ptr), dtype, int(fft_size), int(hop_size),
+                                                           _ptr(window), 1 if projection_back else 0))
 
     def separate_device(self, device_ptr, projection_back=True):
         self._check(self._lib.bss_separate_device(self._h, ctypes.c_void_p(device_ptr), 1 if projection_back else 0))

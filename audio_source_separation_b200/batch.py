@@ -183,11 +183,14 @@ class BatchedGaussILRMA:
         return out if device_out is None else None
 
     def separate_waveform_batch(self, x, fft_size, hop_size=None, window_fn='hann', out=None, iteration=100, basis=None,
-                                activation=None, pipeline='ramp'):
+                                activation=None, pipeline='ramp', device_out=None, loss_out=None):
         """The whole job in the time domain, pipelined like `separate_batch`: x (B,C,n_samples) float32/float64 in host
         memory -> separated signals (B,N,n_out) of the same dtype written to `out` (allocated when None), n_out = the length
         scipy.signal.istft returns.  STFT (src/transform/stft.py:4-8), update loop, projection back and ISTFT (:10-17) run on
-        the device, so only waveforms cross PCIe: half the bytes of the spectrograms at 50 % overlap."""
+        the device, so only waveforms cross PCIe: half the bytes of the spectrograms at 50 % overlap.
+        `device_out`: address of a device buffer (B,N,n_out) of x's dtype on this model's GPU: the separated signals are left
+        there instead of being copied to the host (None is returned).  `loss_out`: a float64 array (B,) that receives the
+        final negative log-likelihood of every mixture (one small device-to-host read per sub-batch)."""
         from scipy import signal as ss
         if x.dtype not in (np.float32, np.float64) or not x.flags.c_contiguous:
             x = np.ascontiguousarray(x, dtype=np.float64)
@@ -198,20 +201,64 @@ class BatchedGaussILRMA:
         F, T = fft_size // 2 + 1, _lib.stft_frames(n_samples, fft_size, hop_size)
         n_out = _lib.istft_length(T, fft_size, hop_size)
         _check_presets(B, C, F, T, self.n_basis, None, basis, activation)
-        if out is None:
-            out = np.empty((B, C, n_out), dtype=x.dtype)
-        if not (out.shape == (B, C, n_out) and out.dtype == x.dtype and out.flags.c_contiguous):
-            raise ValueError("out must be a C-contiguous {} array of shape {}".format(x.dtype, (B, C, n_out)))
+        if device_out is None:
+            if out is None:
+                out = np.empty((B, C, n_out), dtype=x.dtype)
+            if not (out.shape == (B, C, n_out) and out.dtype == x.dtype and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous {} array of shape {}".format(x.dtype, (B, C, n_out)))
+        if loss_out is not None and not (loss_out.shape == (B,) and loss_out.dtype == np.float64):
+            raise ValueError("loss_out must be a float64 array of shape {}".format((B,)))
         dtype = _lib.F32 if x.dtype == np.float32 else _lib.F64
+        esz = x.dtype.itemsize
 
         def feed(h, lo, hi):
             h.set_input_waveform_ptr(x[lo:hi].ctypes.data, dtype, n_samples, fft_size, hop_size, window)
 
         def drain(h, lo, hi):
-            h.separate_waveform_into(out[lo:hi].ctypes.data, dtype, fft_size, hop_size, window, projection_back=True)
+            if device_out is not None:
+                h.separate_waveform_device(int(device_out) + lo * C * n_out * esz, dtype, fft_size, hop_size, window, projection_back=True)
+                if loss_out is None:
+                    h.synchronize()
+            else:
+                h.separate_waveform_into(out[lo:hi].ctypes.data, dtype, fft_size, hop_size, window, projection_back=True)
+            if loss_out is not None:
+                loss_out[lo:hi] = h.loss()   # waits for the stream: everything queued above is complete afterwards
 
         self._pipelined(B, C, F, T, iteration, basis, activation, pipeline, feed, drain)
-        return out
+        return out if device_out is None else None
+
+    def separate_waveform_batch_sharded(self, x, fft_size, hop_size=None, window_fn='hann', iteration=100, basis=None, activation=None,
+                                        group=None, pipeline='ramp', loss_out=None):
+        """BASELINE configs[4] as one call, time domain in / time domain out (one process per GPU, torch.distributed
+        initialised by the caller; without it: one GPU, no collective).  Every rank passes the SAME global description --
+        x (B,C,n_samples) float32/float64 in host memory, of which it reads only its own contiguous shard
+        `shard_range(B, rank, world)` -- uploads its shard pipelined against the update loop (STFT, `iteration` updates,
+        projection back and ISTFT on the device), leaves its separated signals on its GPU and takes part in the one
+        collective of the path: the NCCL all-gather of the separated outputs over NVLink.  Returns a torch tensor
+        (B,N,n_out) of x's dtype on this rank's GPU with the signals of ALL mixtures in batch order.  `loss_out` (B_local,)
+        float64 receives the final losses of this rank's mixtures (the job's device-to-host read)."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        B, C, n_samples = x.shape
+        if hop_size is None:
+            hop_size = fft_size // 2
+        lo, hi = shard_range(B, rank, world)
+        T = _lib.stft_frames(n_samples, fft_size, hop_size)
+        n_out = _lib.istft_length(T, fft_size, hop_size)
+        xl = x[lo:hi]
+        tdtype = torch.float32 if xl.dtype == np.float32 else torch.float64
+        y_local = torch.empty((hi - lo, C, n_out), dtype=tdtype, device=torch.device('cuda', self.device))
+        if hi > lo:
+            self.separate_waveform_batch(xl, fft_size, hop_size, window_fn, iteration=iteration,
+                                         basis=None if basis is None else basis[lo:hi],
+                                         activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
+                                         device_out=y_local.data_ptr(), loss_out=loss_out)
+        if world == 1:
+            return y_local
+        sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
+        return gather_outputs(y_local, world, group=group, sizes=sizes)
 
     def separate_batch_sharded(self, X, iteration=100, basis=None, activation=None, group=None, pipeline='ramp', local_only=False):
         """The multi-GPU whole job (one process per GPU, torch.distributed initialised by the caller): every rank passes the

@@ -498,6 +498,16 @@ int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int h
     return check_flags(h);
 }
 
+int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int fft_size, int hop_size, const double* window,
+                                 int apply_projection_back) {
+    if (!h || !y_device || !window) return BSS_EINVAL;
+    const size_t elems = (size_t)h->B * h->N * h->F * h->T;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    BSS_TRY(ensure_staging(h, elems * 8));
+    BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
+    return istft_from_device(h, (const cf*)h->staging, h->B * h->N, fft_size, hop_size, window, y_device, dtype, 1);
+}
+
 int bss_set_option(bss_handle* h, int option, int value) {
     if (!h) return BSS_EINVAL;
     switch (option) {

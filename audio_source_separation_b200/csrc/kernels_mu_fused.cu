@@ -5,7 +5,7 @@
 // and streams P again for the activation update, because there a warp owns a bin in the first kernel and a frame block in
 // the second.  Here a CTA owns a run of bins of one mixture and each of its warps owns one 128-frame block of EVERY bin
 // of the run: the powers of a lane's frames stay in registers between the two updates, the warps of the CTA exchange
-// only their 16 partial sums of the basis statistics per bin (one CTA barrier), every warp forms the new basis row
+// only their 16 partial sums of the basis statistics per bin (through shared memory and an mbarrier), every warp forms the new basis row
 // and adds the bin's contribution to its activation accumulators.  P never exists in memory: an iteration moves
 // 2 x 8 C F T bytes (this kernel and the covariance kernel) instead of 3 x.
 // The sums over frames are taken lane-butterfly first, then over the warps in block order; the sums over bins chunk by
@@ -19,6 +19,8 @@ namespace {
 
 constexpr int FU_STAGES = 4;      // ring stages per warp (one 128-frame block of one bin + its packed parameters each)
 constexpr int FU_MAX_WARPS = 4;   // frame blocks per bin tile covered by one CTA (Tp <= 512)
+// ring mbarriers + 4 exchange mbarriers + 4 exchange slots of [FU_MAX_WARPS][16] floats, rounded to the 128-byte stage alignment
+constexpr int FU_HEAD_BYTES = (FU_MAX_WARPS * FU_STAGES * 8 + 4 * 8 + 4 * FU_MAX_WARPS * 16 * 4 + 127) / 128 * 128;
 
 struct FusedParams {
     MuArgs a;
@@ -91,17 +93,22 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
     const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.X) + ((size_t)b * a.F * C * Tp + (size_t)blk0 * C) * 8;
     const unsigned char* par0 = p.pbin + (size_t)b * a.F * p.pb_stride;
 
-    // shared memory: [warps][STG] mbarriers | exchange[2][FU_MAX_WARPS][16] floats | [warps][STG] stages
+    // shared memory: [warps][STG] ring mbarriers | 4 exchange mbarriers | exchange[4][FU_MAX_WARPS][16] floats | [warps][STG] stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * STG;
-    float* exch = reinterpret_cast<float*>(smem + FU_MAX_WARPS * STG * 8);
-    unsigned char* ring = smem + FU_MAX_WARPS * STG * 8 + 2 * FU_MAX_WARPS * 16 * 4 + (size_t)warp * STG * p.stage_bytes;
-    const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring);
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem) + FU_MAX_WARPS * STG;
+    float* exch = reinterpret_cast<float*>(smem + FU_HEAD_BYTES - 4 * FU_MAX_WARPS * 16 * 4);
+    unsigned char* ring = smem + FU_HEAD_BYTES + (size_t)warp * STG * p.stage_bytes;
+    const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring), xbar_sa = smem_u32(xbar);
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < STG; ++i) mbar_init(&bars[i], 1);
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mbar_init(&xbar[i], (uint32_t)n_warps);
+        }
         mbar_fence_init();
     }
-    __syncwarp();
+    __syncthreads();   // the exchange barriers are initialised before any warp arrives on them
     auto issue = [&](int f, int stage) {
         if (lane == 0) {
             const uint32_t bar = bars_sa + 8u * (uint32_t)stage;
@@ -140,8 +147,10 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
 
     int cstage = 0;
     uint32_t cphase = 0;
-#pragma unroll 1
-    for (int f = f_begin; f < f_end; ++f) {
+    // Phase 1 of a bin: wait for its block, form the source powers of this lane's frames (returned in P), the basis
+    // statistics with the old basis, reduce them over the lanes, publish the warp's 16 partial sums in exchange slot
+    // (f - f_begin) & 3 and arrive on that slot's mbarrier.  Returns the old basis value of statistic `lane` (lanes < 8).
+    auto phase1 = [&](int f, float2 (&P)[2][N]) -> float {
         if (fp < f_end) {
             issue(fp, pstage);
             ++fp;
@@ -169,9 +178,7 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
         for (int n = 0; n < N; ++n)
 #pragma unroll
             for (int kk = 0; kk < KC; ++kk) tk[n][kk] = tb[n * KC + kk];
-
-        // ---- source powers of this lane's frames, basis statistics with the old basis ---------------------------------
-        float2 P[2][N];
+        const float told = lane < N * KC ? tb[lane] : 0.f;
         float2 tnum[N][KC], tden[N][KC];
 #pragma unroll
         for (int n = 0; n < N; ++n)
@@ -218,9 +225,8 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
                 for (int n = 0; n < N; ++n) P[j][n] = make_float2(0.f, 0.f);
             }
         }
-        __syncwarp();
-
-        // ---- 16 statistics: over the lanes (butterfly), then over the warps in block order ---------------------------
+        // 16 statistics over the lanes (butterfly); the shuffles also order every lane's reads of the stage before the
+        // next copy that lane 0 issues into it
         float flat[16];
 #pragma unroll
         for (int n = 0; n < N; ++n)
@@ -230,20 +236,44 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
                 flat[(n * KC + kk) * 2 + 1] = tden[n][kk].x + tden[n][kk].y;
             }
         const float mine = reduce16(flat, lane);      // lanes 2e, 2e+1: statistic e = (n, k, num | den)
-        float* ex = exch + ((f & 1) * FU_MAX_WARPS + warp) * 16;
+        const int slot = (f - f_begin) & 3;
+        float* ex = exch + (slot * FU_MAX_WARPS + warp) * 16;
         if ((lane & 1) == 0) ex[lane >> 1] = mine;
-        __syncthreads();
-        // lane l < 8 forms the new basis value of (n, k) = l; every warp does (same inputs, same order: identical values)
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xbar_sa + 8u * (uint32_t)slot) : "memory");
+        if (++cstage == STG) {
+            cstage = 0;
+            cphase ^= 1u;
+        }
+        return told;
+    };
+    // Phase 2 of a bin: once every warp has published its partial sums, sum them in block order, form the new basis row
+    // (every warp computes the same values), and add the bin to this lane's activation statistics.
+    auto phase2 = [&](int f, const float2 (&P)[2][N], float told) {
+        const int slot = (f - f_begin) & 3;
+        {
+            const uint32_t bar = xbar_sa + 8u * (uint32_t)slot;
+            const uint32_t parity = (uint32_t)((f - f_begin) >> 2) & 1u;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(parity)
+                    : "memory");
+            }
+        }
         float tnew = 0.f;
         if (lane < N * KC) {
-            const float* e0 = exch + (f & 1) * FU_MAX_WARPS * 16;
+            const float* e0 = exch + slot * FU_MAX_WARPS * 16;
             float nm = 0.f, dn = 0.f;
             for (int g = 0; g < n_warps; ++g) {
                 nm += e0[g * 16 + 2 * lane];
                 dn += e0[g * 16 + 2 * lane + 1];
             }
             dn = fmaxf(dn, a.eps);
-            const float told = tb[lane];
             tnew = told * sqrtf(nm / dn);
             if (warp == 0) a.basis_out[(((size_t)b * N + lane / KC) * a.F + f) * KC + (lane % KC)] = tnew;
         }
@@ -252,8 +282,6 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
         for (int n = 0; n < N; ++n)
 #pragma unroll
             for (int kk = 0; kk < KC; ++kk) tn[n][kk] = __shfl_sync(BSS_FULL, tnew, n * KC + kk);
-
-        // ---- activation statistics with the new basis --------------------------------------------------------------------
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int tt = 2 * lane + 64 * j;
@@ -276,9 +304,20 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
                 }
             }
         }
-        if (++cstage == STG) {
-            cstage = 0;
-            cphase ^= 1u;
+    };
+    // Software pipeline over the bins: phase 1 of bin f + 1 runs before phase 2 of bin f, so a warp meets the partial sums
+    // of the other warps a whole phase after they were due and does not stall on their copies.  Four exchange slots: a warp
+    // can run at most three bins ahead of the slowest one (it needs that warp's arrival for bin f - 1 to start bin f + 1... + 2).
+    float2 Pa[2][N], Pb[2][N];
+    float told_a = 0.f, told_b = 0.f;
+    if (f_begin < f_end) told_a = phase1(f_begin, Pa);
+#pragma unroll 1
+    for (int f = f_begin; f < f_end; f += 2) {
+        if (f + 1 < f_end) told_b = phase1(f + 1, Pb);
+        phase2(f, Pa, told_a);
+        if (f + 1 < f_end) {
+            if (f + 2 < f_end) told_a = phase1(f + 2, Pa);
+            phase2(f + 1, Pb, told_b);
         }
     }
 #pragma unroll
@@ -314,7 +353,7 @@ int launch_mu_fused(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* don
     p.pb_stride = round_up(C * C * 8 + C * KC * 4, 16);
     p.par_off = (uint32_t)round_up(C * blk_frames * 8, 16);
     p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
-    const size_t smem_bytes = (size_t)FU_MAX_WARPS * FU_STAGES * 8 + 2 * FU_MAX_WARPS * 16 * 4 + (size_t)n_blocks * FU_STAGES * p.stage_bytes;
+    const size_t smem_bytes = (size_t)FU_HEAD_BYTES + (size_t)n_blocks * FU_STAGES * p.stage_bytes;
     static bool attr_done = false;
     if (!attr_done) {
         BSS_CUDA(h, cudaFuncSetAttribute(mu_fused_kernel<C, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));

@@ -393,7 +393,8 @@ int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int
 
 // time-domain output of a handle: ISTFT of the separated estimates already sitting on the device as (B, N, F, T) complex64;
 // y (B, N, out_len) float32/float64 on the host.  Scratch lives on the handle (no allocation per call).
-int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, int hop_size, const double* window, void* y, int dtype) {
+int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, int hop_size, const double* window, void* y, int dtype,
+                      int y_on_device) {
     if (!pow2(fft_size) || fft_size < 8 || fft_size > 16384) return bss_fail(h, BSS_EUNSUPPORTED, "fft_size must be a power of two in [8, 16384]");
     if (dtype != BSS_F32 && dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "waveforms are float32 or float64");
     if (fft_size / 2 + 1 != h->F) return bss_fail(h, BSS_EINVAL, "n_bins of the handle must be fft_size / 2 + 1");
@@ -404,9 +405,9 @@ int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, i
     if (handle_tables(h, window, fft_size, &t) != BSS_OK) return bss_fail(h, BSS_ENOMEM, "stft tables");
     const size_t esz = dtype == BSS_F32 ? 4 : 8;
     const size_t frames_bytes = ((size_t)n_signals * n_frames * fft_size * sizeof(float) + 255) / 256 * 256;
-    BSS_TRY(ensure_scratch2(h, frames_bytes + (size_t)n_signals * out_len * esz));
+    BSS_TRY(ensure_scratch2(h, frames_bytes + (y_on_device ? 0 : (size_t)n_signals * out_len * esz)));
     float* frames = (float*)h->scratch2;
-    void* od = (char*)h->scratch2 + frames_bytes;
+    void* od = y_on_device ? y : (void*)((char*)h->scratch2 + frames_bytes);   // overlap-add straight into the caller's device buffer
     IstftParams<float2> p{};
     p.z = z;
     p.win = t.win;
@@ -430,6 +431,7 @@ int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, i
                                                                                hop_size, n_frames, out_len);
     h->launches += 2;
     BSS_CUDA(h, cudaGetLastError());
+    if (y_on_device) return BSS_OK;   // queued on the handle's stream; bss_synchronize when the caller needs it
     BSS_CUDA(h, cudaMemcpyAsync(y, od, (size_t)n * esz, cudaMemcpyDeviceToHost, h->stream));
     BSS_CUDA(h, bss_wait(h));
     return BSS_OK;

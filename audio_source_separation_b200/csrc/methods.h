@@ -46,4 +46,5 @@ int nmf_loss(bss_handle* h);
 
 // STFT feed: kernels_stft.cu
 int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int fft_size, int hop_size, const double* window);
-int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, int hop_size, const double* window, void* y, int dtype);
+int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, int hop_size, const double* window, void* y, int dtype,
+                      int y_on_device = 0);

@@ -12,11 +12,12 @@ resident batch; `value` = mixture-iterations per second = N * B * K / max-over-r
 SAME synthetic mixtures: `mix2(4, 2049, 512, seed)` of SURVEY.md Appendix D, complex64-rounded.
 
   value        device-resident loop, CUDA events on the handle's stream, barrier + sync on both sides
-  e2e          the same job through the public host API from pinned host buffers, host<->device copies inside the timed
-               region: the time-domain job (BatchedGaussILRMA.separate_waveform_batch: waveforms up, STFT + K iterations
-               + projection back + ISTFT on the device, waveforms down).  `e2e_spectrogram` is the same job with the
-               STFT tensors crossing PCIe instead (separate_batch); N > 1 adds `e2e_gather`, the sharded product call
-               (separate_batch_sharded) that ends in the NCCL all-gather of the outputs instead of the D2H copy
+  e2e          BASELINE configs[4] through the public host API, host<->device copies inside the timed region:
+               BatchedGaussILRMA.separate_waveform_batch_sharded -- the rank's waveforms up from pinned host memory, STFT +
+               K iterations + projection back + ISTFT on the device, the separated signals of all ranks gathered over
+               NVLink onto every GPU (the one collective of the path; none at N = 1), the final losses down.
+               `e2e_host_waveform` / `e2e_host_spectrogram` deliver the outputs to pinned host memory instead (waveforms or
+               STFT tensors both ways): those are bound by the host link of the box, not by the GPUs
   roofline     the covariance-accumulate kernel timed alone (CUDA events) against the measured HBM peak
   parity       the timed batch against a single-mixture handle replaying the same iterations (bit exact), and one more
                update_once against the CPU arm's implementation from the same state
@@ -630,52 +631,63 @@ def run_gpu_arm(args):
     timelines = {"spectrogram": getattr(model, 'timeline', None), "waveform": getattr(wave_model, 'timeline', None)}
     del wave_model
 
-    # ---- the sharded product call and its one collective --------------------------------------------
+    # ---- BASELINE configs[4] as one product call: shard up, iterate, NVLink gather of the outputs ----------------------
+    # every rank describes the same global batch; only its own shard is read (here: the rank's pinned buffer)
+    class GlobalWaveforms:   # minimal array protocol: shape + slicing of the local shard
+        shape = (world * B, C, n_samples)
+
+        def __getitem__(self, sl):
+            assert sl.start == rank * B and sl.stop == (rank + 1) * B
+            return w_in
+    gw = GlobalWaveforms()
+    T0g = np.broadcast_to(T0s, (world * B,) + T0s.shape)
+    V0g = np.broadcast_to(V0s, (world * B,) + V0s.shape)
+    losses = np.zeros(B, dtype=np.float64)
+    shard_model = BatchedGaussILRMA(n_basis=K_BASIS, device=local_rank)
+    holder = {}
+
+    def sharded_job():
+        holder['y'] = None   # the previous job's gathered output is released before the next one allocates
+        holder['y'] = shard_model.separate_waveform_batch_sharded(gw, FFT, HOP, iteration=steps, basis=T0g, activation=V0g,
+                                                                  pipeline=pipeline, loss_out=losses)
+        torch.cuda.synchronize()
+    shard_s, shard_runs = timed_jobs(sharded_job)
+    if tuple(holder['y'].shape) != (world * B, C, n_out) or not np.all(np.isfinite(losses)):
+        raise RuntimeError("sharded job: wrong output shape or non-finite loss")
+    timelines["sharded"] = getattr(shard_model, 'timeline', None)
+    holder.clear()
+    del shard_model
+
+    # the all-gather alone, warm: (world - 1) x the per-rank outputs received per GPU
     gather = None
     if dist is not None:
-        # every rank describes the same global batch; only its own shard is read (here: the rank's pinned buffer)
-        class GlobalBatch:   # minimal array protocol: shape + slicing of the local shard
-            shape = (world * B, C, F, T)
-
-            def __getitem__(self, sl):
-                assert sl.start == rank * B and sl.stop == (rank + 1) * B
-                return x_np
-        gb = GlobalBatch()
-        T0g = np.broadcast_to(T0s, (world * B,) + T0s.shape)
-        V0g = np.broadcast_to(V0s, (world * B,) + V0s.shape)
-        g_s, g_runs = timed_jobs(lambda: model.separate_batch_sharded(gb, iteration=steps, basis=T0g, activation=V0g, pipeline=pipeline))
-        # the all-gather alone, warm: 2.15 GB per rank in, (world - 1) x 2.15 GB received per GPU
-        y_dev = torch.empty((B, C, F, T), dtype=torch.complex64, device='cuda')
-        h.separate_device(y_dev.data_ptr(), projection_back=True)
-        h.synchronize()
-        yr = torch.view_as_real(y_dev)
-        gather_outputs(yr, world)   # warm: communicator channels, buffers
-        torch.cuda.synchronize()
-        times = []
-        for _ in range(3):
-            dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            gathered = gather_outputs(yr, world)
-            e1.record()
+        gather = {"nvlink5_unidirectional_GBps": 900.0}
+        for label, shape, dt in (("spectrogram_outputs", (B, C, F, T, 2), torch.float32), ("waveform_outputs", (B, C, n_out), torch.float32)):
+            y_dev = torch.ones(shape, dtype=dt, device='cuda')
+            gather_outputs(y_dev, world)   # warm: communicator channels, buffers
             torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-            assert gathered.shape[0] == world * B
-            del gathered
-        tt = torch.tensor([float(np.median(times))], device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        g_ms = float(tt.item())
-        recv = (world - 1) * B * C * F * T * 8
-        gather = {"ms": g_ms, "bytes_received_per_gpu": recv, "GBps_received_per_gpu": recv / (g_ms * 1e-3) / 1e9,
-                  "nvlink5_unidirectional_GBps": 900.0, "e2e_seconds": g_s,
-                  "e2e_value": world * B * steps / g_s, "e2e_job": "separate_batch_sharded: H2D of the shard + {} iterations + "
-                  "separate / projection back + NCCL all-gather of all {} outputs onto every GPU (no D2H)".format(steps, world * B)}
-        del y_dev
+            times = []
+            for _ in range(3):
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                gathered = gather_outputs(y_dev, world)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+                assert gathered.shape[0] == world * B
+                del gathered
+            tt = torch.tensor([float(np.median(times))], device='cuda')
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            g_ms = float(tt.item())
+            recv = (world - 1) * y_dev.numel() * 4
+            gather[label] = {"ms": g_ms, "bytes_received_per_gpu": recv, "GBps_received_per_gpu": recv / (g_ms * 1e-3) / 1e9}
+            del y_dev
 
     clocks = sampler.stop() if rank == 0 else None
     if os.environ.get('BENCH_TIMELINE'):   # per-rank phase marks of the last end-to-end jobs (diagnostics)
         with open('{}.rank{}.json'.format(os.environ['BENCH_TIMELINE'], rank), 'w') as fh:
-            json.dump({"rank": rank, "world": world, "spectrogram_s": spec_s, "waveform_s": wave_s, "timelines": timelines,
+            json.dump({"rank": rank, "world": world, "spectrogram_s": spec_s, "waveform_s": wave_s, "sharded_s": shard_s, "timelines": timelines,
                        "cpus": len(os.sched_getaffinity(0))}, fh)
 
     if rank == 0:
@@ -719,19 +731,26 @@ def run_gpu_arm(args):
                        "untimed": "{} warm-up + {} graph-priming iterations".format(warmup, GRAPH_PRIME),
                        "l2": "inputs larger than L2 ({:.2f} GB per GPU per pass): no flush".format(B * 8 * C * F * T / 1e9),
                        "storage": "complex64/float32 tensors, float64 per-bin solves",
-                       "e2e_job": "one BatchedGaussILRMA.separate_waveform_batch call (pipelined sub-batches: {}): H2D of the float32 "
-                                  "waveforms ({} samples x 4ch per mixture) from pinned memory + STFT ({}/{}) + {} iterations + "
-                                  "separate/projection-back + ISTFT + D2H of the separated waveforms to pinned memory; bytes amortised "
-                                  "per iteration".format(pipeline, n_samples, FFT, HOP, steps)},
+                       "e2e_job": "BASELINE configs[4] as one call, BatchedGaussILRMA.separate_waveform_batch_sharded (pipelined "
+                                  "sub-batches: {}): H2D of the rank's float32 waveforms ({} samples x 4ch per mixture) from pinned memory + "
+                                  "STFT ({}/{}) + {} iterations + separate/projection-back + ISTFT on the device + NCCL all-gather of all "
+                                  "separated signals onto every GPU (N = 1: no collective, the signals stay on the GPU) + D2H of the "
+                                  "final per-mixture losses; bytes amortised per iteration.  e2e_host_* are the same job with the "
+                                  "outputs delivered to pinned host memory instead (bound by the host link of the box, see "
+                                  "profiles/r6d_pcie_probe_8gpu.json)".format(pipeline, n_samples, FFT, HOP, steps)},
             "clocks": clocks,
-            "e2e": {"value": world * B * steps / wave_s, "unit": "iterations/s", "h2d_bytes_per_step": wave_h2d / steps,
-                    "d2h_bytes_per_step": wave_d2h / steps, "seconds": wave_s, "seconds_per_job": [round(v, 6) for v in wave_runs],
-                    "input": "waveforms (time domain in, time domain out)"},
-            "e2e_spectrogram": {"value": world * B * steps / spec_s, "unit": "iterations/s", "h2d_bytes_per_step": x_host.numel() * 8 / steps,
-                                "d2h_bytes_per_step": y_host.numel() * 8 / steps, "seconds": spec_s,
-                                "seconds_per_job": [round(v, 6) for v in spec_runs],
-                                "job": "BatchedGaussILRMA.separate_batch: complex64 STFT tensors up, separated STFT tensors down"},
-            "e2e_gather": gather,
+            "e2e": {"value": world * B * steps / shard_s, "unit": "iterations/s", "h2d_bytes_per_step": wave_h2d / steps,
+                    "d2h_bytes_per_step": B * 8 / steps, "seconds": shard_s, "seconds_per_job": [round(v, 6) for v in shard_runs],
+                    "job": "separate_waveform_batch_sharded: waveforms up, separated waveforms gathered over NVLink onto every GPU, "
+                           "losses down"},
+            "e2e_host_waveform": {"value": world * B * steps / wave_s, "unit": "iterations/s", "h2d_bytes_per_step": wave_h2d / steps,
+                                  "d2h_bytes_per_step": wave_d2h / steps, "seconds": wave_s, "seconds_per_job": [round(v, 6) for v in wave_runs],
+                                  "job": "separate_waveform_batch: waveforms up, separated waveforms down to pinned host memory"},
+            "e2e_host_spectrogram": {"value": world * B * steps / spec_s, "unit": "iterations/s", "h2d_bytes_per_step": x_host.numel() * 8 / steps,
+                                     "d2h_bytes_per_step": y_host.numel() * 8 / steps, "seconds": spec_s,
+                                     "seconds_per_job": [round(v, 6) for v in spec_runs],
+                                     "job": "separate_batch: complex64 STFT tensors up, separated STFT tensors down to pinned host memory"},
+            "gather": gather,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "cov_kernel<C=4,NS=4,WM_ILRMA,K=2,CACHE>", "launch_ms": cov_ms, "algorithmic_bytes": cov_bytes,

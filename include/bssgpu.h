@@ -229,6 +229,10 @@ int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int h
 /* per-handle switches and read-outs, see enum bss_option / enum bss_info */
 int bss_set_option(bss_handle* h, int option, int value);
 int bss_get_info(bss_handle* h, int what, int64_t* value);
+/* the same with the time-domain estimates left on the device: y_device (B,N,bss_istft_length(...)) float32/float64; queued on
+ * the handle's stream (bss_synchronize before another stream reads it) -- feeds the NCCL gather of a sharded batch */
+int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int fft_size, int hop_size, const double* window,
+                                 int apply_projection_back);
 /* ISS keeps no filter: W = Y X^H (X X^H)^-1 (src/bss/ilrma.py:167-173); result is readable as
  * BSS_STATE_DEMIX_FILTER afterwards */
 int bss_compute_demix_filter(bss_handle* h);

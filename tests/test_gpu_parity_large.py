@@ -319,7 +319,7 @@ def test_projection_back_reference_signature(cuda_device):
         projection_back(np.zeros_like(Yr), ref)
 
 
-@pytest.mark.parametrize('F,T', [(40, 131), (17, 512), (9, 385), (5, 2), (33, 48), (150, 200)])
+@pytest.mark.parametrize('F,T', [(40, 131), (17, 512), (9, 385), (5, 6), (33, 48), (150, 200), (300, 64)])
 def test_fused_source_model_against_oracle_and_three_pass(cuda_device, F, T):
     """The single-pass source-model kernel (kernels_mu_fused.cu: basis and activation update from one stream over X) on
     whole-block, ragged and odd frame counts: against the oracle (src/bss/ilrma.py:413-428) and against the three-pass form
