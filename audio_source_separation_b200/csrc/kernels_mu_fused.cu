@@ -5,22 +5,23 @@
 // and streams P again for the activation update, because there a warp owns a bin in the first kernel and a frame block in
 // the second.  Here a CTA owns a run of bins of one mixture and each of its warps owns one 128-frame block of EVERY bin
 // of the run: the powers of a lane's frames stay in registers between the two updates, the warps of the CTA exchange
-// only their 16 partial sums of the basis statistics per bin (through shared memory and an mbarrier), every warp forms the new basis row
+// only their 16 partial sums of the basis statistics per bin (one CTA barrier), every warp forms the new basis row
 // and adds the bin's contribution to its activation accumulators.  P never exists in memory: an iteration moves
 // 2 x 8 C F T bytes (this kernel and the covariance kernel) instead of 3 x.
 // The sums over frames are taken lane-butterfly first, then over the warps in block order; the sums over bins chunk by
 // chunk in mu_act_finish_kernel (kernels_mu.cu): deterministic, and independent of the batch size for a fixed chunk count.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "handle.h"
 
 namespace {
 
-constexpr int FU_STAGES = 4;      // ring stages per warp (one 128-frame block of one bin + its packed parameters each)
+constexpr int FU_STAGES = 4;      // ring stages per warp (one 128-frame block of one bin + its packed parameters each); 3 when four CTAs share an SM
 constexpr int FU_MAX_WARPS = 4;   // frame blocks per bin tile covered by one CTA (Tp <= 512)
-// ring mbarriers + 4 exchange mbarriers + 4 exchange slots of [FU_MAX_WARPS][16] floats, rounded to the 128-byte stage alignment
-constexpr int FU_HEAD_BYTES = (FU_MAX_WARPS * FU_STAGES * 8 + 4 * 8 + 4 * FU_MAX_WARPS * 16 * 4 + 127) / 128 * 128;
+// shared-memory head: [FU_MAX_WARPS][FU_STAGES] ring mbarriers, then exchange[2][FU_MAX_WARPS][16] floats; the stages follow
+constexpr int FU_HEAD_BYTES = (FU_MAX_WARPS * FU_STAGES * 8 + 2 * FU_MAX_WARPS * 16 * 4 + 127) / 128 * 128;
 
 struct FusedParams {
     MuArgs a;
@@ -72,12 +73,13 @@ __device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
 }
 
 // One CTA = blockDim.x / 32 = n_blocks warps; warp g owns frame block g of the bins [f_begin, f_end) of mixture b.
-template <int C, int KC>
-__global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const FusedParams p) {
+// MINB: resident CTAs per SM the register allocation aims at (2: 204 registers, 3: 168, 4: 128 with a few spills)
+template <int C, int KC, int MINB>
+__global__ void __launch_bounds__(FU_MAX_WARPS * 32, MINB) mu_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     static_assert(C * KC * 2 == 16, "the partial-sum exchange is laid out for 16 statistics per bin (C = 4, K = 2)");
     constexpr int N = C;
-    constexpr int STG = FU_STAGES;
+    constexpr int STG = MINB >= 4 ? FU_STAGES - 1 : FU_STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
     const MuArgs& a = p.a;
@@ -93,22 +95,17 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
     const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.X) + ((size_t)b * a.F * C * Tp + (size_t)blk0 * C) * 8;
     const unsigned char* par0 = p.pbin + (size_t)b * a.F * p.pb_stride;
 
-    // shared memory: [warps][STG] ring mbarriers | 4 exchange mbarriers | exchange[4][FU_MAX_WARPS][16] floats | [warps][STG] stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * STG;
-    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem) + FU_MAX_WARPS * STG;
-    float* exch = reinterpret_cast<float*>(smem + FU_HEAD_BYTES - 4 * FU_MAX_WARPS * 16 * 4);
+    // shared memory: [warps][STG] mbarriers | exchange[2][FU_MAX_WARPS][16] floats | [warps][STG] stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * FU_STAGES;
+    float* exch = reinterpret_cast<float*>(smem + FU_MAX_WARPS * FU_STAGES * 8);
     unsigned char* ring = smem + FU_HEAD_BYTES + (size_t)warp * STG * p.stage_bytes;
-    const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring), xbar_sa = smem_u32(xbar);
+    const uint32_t bars_sa = smem_u32(bars), ring_sa = smem_u32(ring);
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < STG; ++i) mbar_init(&bars[i], 1);
-        if (warp == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mbar_init(&xbar[i], (uint32_t)n_warps);
-        }
         mbar_fence_init();
     }
-    __syncthreads();   // the exchange barriers are initialised before any warp arrives on them
+    __syncwarp();
     auto issue = [&](int f, int stage) {
         if (lane == 0) {
             const uint32_t bar = bars_sa + 8u * (uint32_t)stage;
@@ -145,12 +142,14 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
             }
     }
 
+    int tts[2];   // first frame of this lane's pairs inside the block, clamped for lanes past the end of a ragged block
+#pragma unroll
+    for (int j = 0; j < 2; ++j) tts[j] = (2 * lane + 64 * j) < L ? 2 * lane + 64 * j : 0;
+
     int cstage = 0;
     uint32_t cphase = 0;
-    // Phase 1 of a bin: wait for its block, form the source powers of this lane's frames (returned in P), the basis
-    // statistics with the old basis, reduce them over the lanes, publish the warp's 16 partial sums in exchange slot
-    // (f - f_begin) & 3 and arrive on that slot's mbarrier.  Returns the old basis value of statistic `lane` (lanes < 8).
-    auto phase1 = [&](int f, float2 (&P)[2][N]) -> float {
+#pragma unroll 1
+    for (int f = f_begin; f < f_end; ++f) {
         if (fp < f_end) {
             issue(fp, pstage);
             ++fp;
@@ -178,55 +177,59 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
         for (int n = 0; n < N; ++n)
 #pragma unroll
             for (int kk = 0; kk < KC; ++kk) tk[n][kk] = tb[n * KC + kk];
-        const float told = lane < N * KC ? tb[lane] : 0.f;
+
+        // ---- source powers of this lane's frames, basis statistics with the old basis ---------------------------------
+        // (no per-lane branches: lanes past the end of a ragged block read frame 0 instead; their activation values are
+        // zero, so they add nothing to the basis statistics, and their activation statistics are never stored)
+        float2 P[2][N];
         float2 tnum[N][KC], tden[N][KC];
+        float4 xv[2][C];
 #pragma unroll
-        for (int n = 0; n < N; ++n)
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) xv[j][c] = *reinterpret_cast<const float4*>(xs + c * L + tts[j]);
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            float2 y[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) y[j][0] = y[j][1] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                // w x = x * w.x + (-x.y, x.x) * w.y   (the operation order of frame_power2, kernels_mu.cu)
+                const float2 w = wf[n * C + c];
+                const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float2 x0 = make_float2(xv[j][c].x, xv[j][c].y), x1 = make_float2(xv[j][c].z, xv[j][c].w);
+                    y[j][0] = __ffma2_rn(x0, wx, y[j][0]);
+                    y[j][0] = __ffma2_rn(make_float2(-x0.y, x0.x), wy, y[j][0]);
+                    y[j][1] = __ffma2_rn(x1, wx, y[j][1]);
+                    y[j][1] = __ffma2_rn(make_float2(-x1.y, x1.x), wy, y[j][1]);
+                }
+            }
 #pragma unroll
             for (int kk = 0; kk < KC; ++kk) tnum[n][kk] = tden[n][kk] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int tt = 2 * lane + 64 * j;
-            if (tt < L) {
-                float4 xv[C];
+            for (int j = 0; j < 2; ++j) {
+                const float2 s0 = __fmul2_rn(y[j][0], y[j][0]), s1 = __fmul2_rn(y[j][1], y[j][1]);
+                P[j][n] = make_float2(s0.x + s0.y, s1.x + s1.y);
+                float2 tv = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (size_t)c * L + tt);
+                for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tk[n][kk], tk[n][kk]), tv);
+                tv.x = fmaxf(tv.x, a.eps);
+                tv.y = fmaxf(tv.y, a.eps);
+                const float2 sb = rcp2f(tv);
+                const float2 sa = __fmul2_rn(P[j][n], __fmul2_rn(sb, sb));   // P / TV^2
 #pragma unroll
-                for (int n = 0; n < N; ++n) {
-                    float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        // w x = x * w.x + (-x.y, x.x) * w.y   (the operation order of frame_power2, kernels_mu.cu)
-                        const float2 w = wf[n * C + c];
-                        const float2 x0 = make_float2(xv[c].x, xv[c].y), x1 = make_float2(xv[c].z, xv[c].w);
-                        const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
-                        y0 = __ffma2_rn(x0, wx, y0);
-                        y0 = __ffma2_rn(make_float2(-x0.y, x0.x), wy, y0);
-                        y1 = __ffma2_rn(x1, wx, y1);
-                        y1 = __ffma2_rn(make_float2(-x1.y, x1.x), wy, y1);
-                    }
-                    const float2 s0 = __fmul2_rn(y0, y0), s1 = __fmul2_rn(y1, y1);
-                    P[j][n] = make_float2(s0.x + s0.y, s1.x + s1.y);
-                    float2 tv = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tk[n][kk], tk[n][kk]), tv);
-                    tv.x = fmaxf(tv.x, a.eps);
-                    tv.y = fmaxf(tv.y, a.eps);
-                    const float2 sb = rcp2f(tv);
-                    const float2 sa = __fmul2_rn(P[j][n], __fmul2_rn(sb, sb));   // P / TV^2
-#pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) {
-                        tnum[n][kk] = __ffma2_rn(sa, vreg[j][n][kk], tnum[n][kk]);
-                        tden[n][kk] = __ffma2_rn(sb, vreg[j][n][kk], tden[n][kk]);
-                    }
+                for (int kk = 0; kk < KC; ++kk) {
+                    tnum[n][kk] = __ffma2_rn(sa, vreg[j][n][kk], tnum[n][kk]);
+                    tden[n][kk] = __ffma2_rn(sb, vreg[j][n][kk], tden[n][kk]);
                 }
-            } else {
-#pragma unroll
-                for (int n = 0; n < N; ++n) P[j][n] = make_float2(0.f, 0.f);
             }
         }
-        // 16 statistics over the lanes (butterfly); the shuffles also order every lane's reads of the stage before the
-        // next copy that lane 0 issues into it
+        __syncwarp();
+
+        // ---- 16 statistics: over the lanes (butterfly), then over the warps in block order ---------------------------
         float flat[16];
 #pragma unroll
         for (int n = 0; n < N; ++n)
@@ -236,44 +239,20 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
                 flat[(n * KC + kk) * 2 + 1] = tden[n][kk].x + tden[n][kk].y;
             }
         const float mine = reduce16(flat, lane);      // lanes 2e, 2e+1: statistic e = (n, k, num | den)
-        const int slot = (f - f_begin) & 3;
-        float* ex = exch + (slot * FU_MAX_WARPS + warp) * 16;
+        float* ex = exch + ((f & 1) * FU_MAX_WARPS + warp) * 16;
         if ((lane & 1) == 0) ex[lane >> 1] = mine;
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(xbar_sa + 8u * (uint32_t)slot) : "memory");
-        if (++cstage == STG) {
-            cstage = 0;
-            cphase ^= 1u;
-        }
-        return told;
-    };
-    // Phase 2 of a bin: once every warp has published its partial sums, sum them in block order, form the new basis row
-    // (every warp computes the same values), and add the bin to this lane's activation statistics.
-    auto phase2 = [&](int f, const float2 (&P)[2][N], float told) {
-        const int slot = (f - f_begin) & 3;
-        {
-            const uint32_t bar = xbar_sa + 8u * (uint32_t)slot;
-            const uint32_t parity = (uint32_t)((f - f_begin) >> 2) & 1u;
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(bar), "r"(parity)
-                    : "memory");
-            }
-        }
+        __syncthreads();
+        // lane l < 8 forms the new basis value of (n, k) = l; every warp does (same inputs, same order: identical values)
         float tnew = 0.f;
         if (lane < N * KC) {
-            const float* e0 = exch + slot * FU_MAX_WARPS * 16;
+            const float* e0 = exch + (f & 1) * FU_MAX_WARPS * 16;
             float nm = 0.f, dn = 0.f;
             for (int g = 0; g < n_warps; ++g) {
                 nm += e0[g * 16 + 2 * lane];
                 dn += e0[g * 16 + 2 * lane + 1];
             }
             dn = fmaxf(dn, a.eps);
+            const float told = tb[lane];
             tnew = told * sqrtf(nm / dn);
             if (warp == 0) a.basis_out[(((size_t)b * N + lane / KC) * a.F + f) * KC + (lane % KC)] = tnew;
         }
@@ -282,42 +261,30 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
         for (int n = 0; n < N; ++n)
 #pragma unroll
             for (int kk = 0; kk < KC; ++kk) tn[n][kk] = __shfl_sync(BSS_FULL, tnew, n * KC + kk);
+
+        // ---- activation statistics with the new basis --------------------------------------------------------------------
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int tt = 2 * lane + 64 * j;
-            if (tt < L) {
 #pragma unroll
-                for (int n = 0; n < N; ++n) {
-                    float2 tv = make_float2(0.f, 0.f);
+            for (int n = 0; n < N; ++n) {
+                float2 tv = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tn[n][kk], tn[n][kk]), tv);
-                    tv.x = fmaxf(tv.x, a.eps);
-                    tv.y = fmaxf(tv.y, a.eps);
-                    const float2 sb = rcp2f(tv);
-                    const float2 sa = __fmul2_rn(P[j][n], __fmul2_rn(sb, sb));
+                for (int kk = 0; kk < KC; ++kk) tv = __ffma2_rn(vreg[j][n][kk], make_float2(tn[n][kk], tn[n][kk]), tv);
+                tv.x = fmaxf(tv.x, a.eps);
+                tv.y = fmaxf(tv.y, a.eps);
+                const float2 sb = rcp2f(tv);
+                const float2 sa = __fmul2_rn(P[j][n], __fmul2_rn(sb, sb));
 #pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) {
-                        const float2 t2 = make_float2(tn[n][kk], tn[n][kk]);
-                        vnum[j][n][kk] = __ffma2_rn(sa, t2, vnum[j][n][kk]);
-                        vden[j][n][kk] = __ffma2_rn(sb, t2, vden[j][n][kk]);
-                    }
+                for (int kk = 0; kk < KC; ++kk) {
+                    const float2 t2 = make_float2(tn[n][kk], tn[n][kk]);
+                    vnum[j][n][kk] = __ffma2_rn(sa, t2, vnum[j][n][kk]);
+                    vden[j][n][kk] = __ffma2_rn(sb, t2, vden[j][n][kk]);
                 }
             }
         }
-    };
-    // Software pipeline over the bins: phase 1 of bin f + 1 runs before phase 2 of bin f, so a warp meets the partial sums
-    // of the other warps a whole phase after they were due and does not stall on their copies.  Four exchange slots: a warp
-    // can run at most three bins ahead of the slowest one (it needs that warp's arrival for bin f - 1 to start bin f + 1... + 2).
-    float2 Pa[2][N], Pb[2][N];
-    float told_a = 0.f, told_b = 0.f;
-    if (f_begin < f_end) told_a = phase1(f_begin, Pa);
-#pragma unroll 1
-    for (int f = f_begin; f < f_end; f += 2) {
-        if (f + 1 < f_end) told_b = phase1(f + 1, Pb);
-        phase2(f, Pa, told_a);
-        if (f + 1 < f_end) {
-            if (f + 2 < f_end) told_a = phase1(f + 2, Pa);
-            phase2(f + 1, Pb, told_b);
+        if (++cstage == STG) {
+            cstage = 0;
+            cphase ^= 1u;
         }
     }
 #pragma unroll
@@ -336,16 +303,11 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, 2) mu_fused_kernel(const Fu
     }
 }
 
-}  // namespace
-
-// Basis update (into a.basis_out) and the activation statistics (into h->part, *n_chunks_out chunks) in one pass over X.
-// *done = false when the configuration is not covered (the caller then runs the three-pass form).
-int launch_mu_fused(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done) {
-    *done = false;
+template <int MINB>
+static int launch_mu_fused_t(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done) {
     constexpr int C = 4, KC = 2;
-    if (a.C != C || a.K != KC || a.Y || a.raw || a.sel_m >= 0 || a.mode != 0 || a.p_exp != 2.f || a.q_exp != 0.5f) return BSS_OK;
+    constexpr int STG = MINB >= 4 ? FU_STAGES - 1 : FU_STAGES;
     const int n_blocks = (a.Tp + BSS_XSLAB - 1) / BSS_XSLAB;
-    if (n_blocks > FU_MAX_WARPS || a.Tp < 2) return BSS_OK;
     FusedParams p{};
     p.a = a;
     p.n_blocks = n_blocks;
@@ -353,14 +315,14 @@ int launch_mu_fused(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* don
     p.pb_stride = round_up(C * C * 8 + C * KC * 4, 16);
     p.par_off = (uint32_t)round_up(C * blk_frames * 8, 16);
     p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
-    const size_t smem_bytes = (size_t)FU_HEAD_BYTES + (size_t)n_blocks * FU_STAGES * p.stage_bytes;
+    const size_t smem_bytes = (size_t)FU_HEAD_BYTES + (size_t)n_blocks * STG * p.stage_bytes;
     static bool attr_done = false;
     if (!attr_done) {
-        BSS_CUDA(h, cudaFuncSetAttribute(mu_fused_kernel<C, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+        BSS_CUDA(h, cudaFuncSetAttribute(mu_fused_kernel<C, KC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
         attr_done = true;
     }
     int ctas_per_sm = 1;
-    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_fused_kernel<C, KC>, n_blocks * 32, smem_bytes));
+    BSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mu_fused_kernel<C, KC, MINB>, n_blocks * 32, smem_bytes));
     if (ctas_per_sm < 1) return BSS_OK;
     // bin chunks: whole waves of CTAs, chunks of at least 16 bins, at most 4 waves (ties: fewer chunks = fewer partial sums)
     const long long slots = (long long)h->n_sm * ctas_per_sm;
@@ -397,11 +359,31 @@ int launch_mu_fused(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* don
                                                                         p.pb_stride);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
-    mu_fused_kernel<C, KC><<<(unsigned)n_ctas, n_blocks * 32, smem_bytes, h->stream>>>(p);
+    mu_fused_kernel<C, KC, MINB><<<(unsigned)n_ctas, n_blocks * 32, smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
     if (n_chunks_out) *n_chunks_out = p.n_chunks;
     h->last_act_chunks = p.n_chunks;
     *done = true;
     return BSS_OK;
+}
+
+}  // namespace
+
+// Basis update (into a.basis_out) and the activation statistics (into h->part, *n_chunks_out chunks) in one pass over X.
+// *done = false when the configuration is not covered (the caller then runs the three-pass form).
+int launch_mu_fused(bss_handle* h, const MuArgs& a, int* n_chunks_out, bool* done) {
+    *done = false;
+    if (a.C != 4 || a.K != 2 || a.Y || a.raw || a.sel_m >= 0 || a.mode != 0 || a.p_exp != 2.f || a.q_exp != 0.5f) return BSS_OK;
+    const int n_blocks = (a.Tp + BSS_XSLAB - 1) / BSS_XSLAB;
+    if (n_blocks > FU_MAX_WARPS || a.Tp < 2) return BSS_OK;
+    // resident CTAs per SM the kernel is compiled for (measurement aid: BSSGPU_FUSED_CTAS = 2, 3 or 4)
+    static const int ctas = [] {
+        const char* e = getenv("BSSGPU_FUSED_CTAS");
+        const int v = e ? atoi(e) : 3;
+        return v >= 2 && v <= 4 ? v : 3;
+    }();
+    if (ctas == 2) return launch_mu_fused_t<2>(h, a, n_chunks_out, done);
+    if (ctas == 4) return launch_mu_fused_t<4>(h, a, n_chunks_out, done);
+    return launch_mu_fused_t<3>(h, a, n_chunks_out, done);
 }

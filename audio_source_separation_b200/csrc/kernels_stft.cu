@@ -16,20 +16,90 @@ namespace {
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place (ping-pong) forward FFT of length M = N / 2 held in `a`; returns the buffer holding the result
+// Shared-memory index with one pad element per 16 (a 128-byte row of float2): the strided stores of the Stockham passes
+// (stride radix x Ns elements) would otherwise fall on two banks.
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// forward DFTs of size 2 / 4 / 8 in registers, outputs in natural order
+__device__ __forceinline__ void dft4(float2& u0, float2& u1, float2& u2, float2& u3) {
+    const float2 a0 = cadd(u0, u2), a1 = csub(u0, u2), a2 = cadd(u1, u3), a3 = mul_mi(csub(u1, u3));
+    u0 = cadd(a0, a2);
+    u1 = cadd(a1, a3);
+    u2 = csub(a0, a2);
+    u3 = csub(a1, a3);
+}
+__device__ __forceinline__ void dft8(float2 (&u)[8]) {
+    float2 e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6], o0 = u[1], o1 = u[3], o2 = u[5], o3 = u[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    const float h = 0.70710678118654752440f;
+    // odd[q] * exp(-2 pi i q / 8)
+    o1 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));      // (1 - i) / sqrt 2
+    o2 = mul_mi(o2);                                             // -i
+    o3 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));     // (-1 - i) / sqrt 2
+    u[0] = cadd(e0, o0);
+    u[4] = csub(e0, o0);
+    u[1] = cadd(e1, o1);
+    u[5] = csub(e1, o1);
+    u[2] = cadd(e2, o2);
+    u[6] = csub(e2, o2);
+    u[3] = cadd(e3, o3);
+    u[7] = csub(e3, o3);
+}
+
+// One Stockham pass of radix R over M points: a -> b (both padded with fpad).  tw is the full circle exp(-2 pi i m / N),
+// m < N = 2 M, so the twiddle exp(-2 pi i r k / (Ns R)) is tw[r k (N / (Ns R))].
+template <int R>
+__device__ __forceinline__ void stockham_pass(const float2* a, float2* b, const float2* tw, int M, int Ns) {
+    const int per = M / R;
+    const int tstep = (2 * M) / (Ns * R);
+    for (int j = threadIdx.x; j < per; j += blockDim.x) {
+        const int k = j & (Ns - 1);
+        float2 u[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = a[fpad(j + r * per)];
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) u[r] = cmulf(u[r], __ldg(tw + r * k * tstep));
+        }
+        if constexpr (R == 8) {
+            dft8(u);
+        } else if constexpr (R == 4) {
+            dft4(u[0], u[1], u[2], u[3]);
+        } else {
+            const float2 x = u[0], y = u[1];
+            u[0] = cadd(x, y);
+            u[1] = csub(x, y);
+        }
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) b[fpad(j0 + r * Ns)] = u[r];
+    }
+}
+
+// forward FFT of length M = N / 2 (a power of two >= 4) held in `a` (padded layout, see fpad); ping-pongs between a and b
+// and returns the buffer holding the result.  Radix-8 passes, then one radix-4 or radix-2 pass for what is left.
 __device__ __forceinline__ float2* fft_stockham(float2* a, float2* b, const float2* tw, int N) {
     const int M = N >> 1;
-    for (int Ns = 1; Ns < M; Ns <<= 1) {
-        const int tstep = N / (2 * Ns);
-        for (int j = threadIdx.x; j < (M >> 1); j += blockDim.x) {
-            const int k = j & (Ns - 1);
-            const float2 w = __ldg(tw + k * tstep);
-            const float2 x = a[j];
-            const float2 y = cmulf(a[j + (M >> 1)], w);
-            const int j0 = ((j - k) << 1) + k;
-            b[j0] = make_float2(x.x + y.x, x.y + y.y);
-            b[j0 + Ns] = make_float2(x.x - y.x, x.y - y.y);
+    int Ns = 1;
+    while (Ns < M) {
+        const int rest = M / Ns;
+        int R;
+        if (rest >= 8 && rest != 16) {   // 16 = 4 x 4 (two passes either way, radix 4 keeps all threads busy)
+            stockham_pass<8>(a, b, tw, M, Ns);
+            R = 8;
+        } else if (rest >= 4) {
+            stockham_pass<4>(a, b, tw, M, Ns);
+            R = 4;
+        } else {
+            stockham_pass<2>(a, b, tw, M, Ns);
+            R = 2;
         }
+        Ns *= R;
         __syncthreads();
         float2* t = a;
         a = b;
@@ -41,7 +111,7 @@ __device__ __forceinline__ float2* fft_stockham(float2* a, float2* b, const floa
 struct StftParams {
     const float* x;      // [S][n_samples]
     const float* win;    // [N]
-    const float2* tw;    // [N/2]  exp(-2 pi i m / N)
+    const float2* tw;    // [N]  exp(-2 pi i m / N), the full circle
     int S, n_samples, N, hop, n_frames;
     float scale;         // 1 / sum(window)
     double2* out128;     // [S][N/2+1][n_frames]   (reference layout) or null
@@ -53,7 +123,7 @@ __global__ void __launch_bounds__(1024) stft_kernel(const StftParams p) {
     extern __shared__ __align__(16) float2 fft_smem[];
     const int N = p.N, M = N >> 1;
     float2* a = fft_smem;
-    float2* b = fft_smem + M;
+    float2* b = fft_smem + fpad(M) + 1;
     const int frame = blockIdx.x, s = blockIdx.y;
     const float* x = p.x + (size_t)s * p.n_samples;
     const int start = frame * p.hop - (N >> 1);   // position of the frame in the unextended signal
@@ -61,13 +131,13 @@ __global__ void __launch_bounds__(1024) stft_kernel(const StftParams p) {
         const int i0 = start + 2 * j, i1 = i0 + 1;
         const float v0 = (i0 >= 0 && i0 < p.n_samples) ? x[i0] * p.win[2 * j] : 0.f;
         const float v1 = (i1 >= 0 && i1 < p.n_samples) ? x[i1] * p.win[2 * j + 1] : 0.f;
-        a[j] = make_float2(v0, v1);
+        a[fpad(j)] = make_float2(v0, v1);
     }
     __syncthreads();
     const float2* Z = fft_stockham(a, b, p.tw, N);
     for (int k = threadIdx.x; k <= M; k += blockDim.x) {
-        const float2 zk = Z[k == M ? 0 : k];
-        const float2 zm = Z[k == 0 ? 0 : M - k];
+        const float2 zk = Z[fpad(k == M ? 0 : k)];
+        const float2 zm = Z[fpad(k == 0 ? 0 : M - k)];
         const float2 w = k < M ? __ldg(p.tw + k) : make_float2(-1.f, 0.f);
         // X[k] = (Zk + conj(Zm)) / 2 - (i / 2) w (Zk - conj(Zm))
         const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
@@ -97,7 +167,7 @@ __global__ void __launch_bounds__(1024) istft_frames_kernel(const IstftParams<TZ
     extern __shared__ __align__(16) float2 fft_smem[];
     const int N = p.N, M = N >> 1;
     float2* a = fft_smem;
-    float2* b = fft_smem + M;
+    float2* b = fft_smem + fpad(M) + 1;
     const int frame = blockIdx.x, s = blockIdx.y;
     const TZ* z = p.z + (size_t)s * (M + 1) * p.n_frames + frame;
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
@@ -108,13 +178,13 @@ __global__ void __launch_bounds__(1024) istft_frames_kernel(const IstftParams<TZ
         const float2 e = make_float2(0.5f * (float)(xk.x + xm.x), 0.5f * (float)(xk.y - xm.y));
         const float2 o = make_float2(0.5f * (float)(xk.x - xm.x), 0.5f * (float)(xk.y + xm.y));
         const float2 wo = cmulf(make_float2(w.x, -w.y), o);
-        a[k] = make_float2(e.x - wo.y, -(e.y + wo.x));
+        a[fpad(k)] = make_float2(e.x - wo.y, -(e.y + wo.x));
     }
     __syncthreads();
     const float2* Z = fft_stockham(a, b, p.tw, N);
     float* out = p.frames + ((size_t)s * p.n_frames + frame) * N;
     for (int j = threadIdx.x; j < M; j += blockDim.x) {
-        const float2 v = Z[j];   // conj(v) / M is the time signal pair
+        const float2 v = Z[fpad(j)];   // conj(v) / M is the time signal pair
         out[2 * j] = v.x * p.scale * p.win[2 * j];
         out[2 * j + 1] = -v.y * p.scale * p.win[2 * j + 1];
     }
@@ -157,18 +227,18 @@ struct FftTables {
 
 int make_tables(const double* window, int N, cudaStream_t stream, FftTables* t) {
     std::vector<float> w(N);
-    std::vector<float2> tw(N / 2);
+    std::vector<float2> tw(N);   // the full circle: the radix-8 passes use exp(-2 pi i m / N) up to m = 7 N / 8
     double sum = 0.0;
     for (int i = 0; i < N; ++i) {
         w[i] = (float)window[i];
         sum += window[i];
     }
     const double pi = 3.14159265358979323846;
-    for (int m = 0; m < N / 2; ++m) tw[m] = make_float2((float)cos(-2.0 * pi * m / N), (float)sin(-2.0 * pi * m / N));
+    for (int m = 0; m < N; ++m) tw[m] = make_float2((float)cos(-2.0 * pi * m / N), (float)sin(-2.0 * pi * m / N));
     if (cudaMalloc(&t->win, N * sizeof(float)) != cudaSuccess) return BSS_ENOMEM;
-    if (cudaMalloc(&t->tw, (N / 2) * sizeof(float2)) != cudaSuccess) return BSS_ENOMEM;
+    if (cudaMalloc(&t->tw, N * sizeof(float2)) != cudaSuccess) return BSS_ENOMEM;
     cudaMemcpyAsync(t->win, w.data(), N * sizeof(float), cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(t->tw, tw.data(), (N / 2) * sizeof(float2), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(t->tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice, stream);
     cudaStreamSynchronize(stream);   // the host vectors go out of scope
     t->win_sum = sum;
     return BSS_OK;
@@ -179,12 +249,15 @@ void free_tables(FftTables* t) {
     if (t->tw) cudaFree(t->tw);
 }
 
+// one thread per radix-8 butterfly of the M = N / 2 point transform
 int fft_threads(int N) {
-    int th = N / 4;
+    int th = N / 16;
     if (th < 32) th = 32;
     if (th > 1024) th = 1024;
     return th;
 }
+// two padded buffers of M = N / 2 float2 (fpad)
+size_t fft_smem_bytes(int N) { return (size_t)(2 * ((N / 2) + (N / 2) / 16 + 2)) * sizeof(float2); }
 
 }  // namespace
 
@@ -245,7 +318,7 @@ static int stft_common(int device, cudaStream_t stream, int S, int n_samples, in
     p.X = X;
     p.C = C;
     p.Tp = Tp;
-    const size_t smem = (size_t)fft_size * sizeof(float2);
+    const size_t smem = fft_smem_bytes(fft_size);
     cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(n_frames, S);
     stft_kernel<<<grid, fft_threads(fft_size), smem, stream>>>(p);
@@ -300,7 +373,7 @@ int bss_istft(int device, int n_signals, int n_frames, int fft_size, int hop_siz
         p.n_frames = n_frames;
         p.scale = (float)(t.win_sum / (double)(fft_size / 2));
         p.frames = frames;
-        const size_t smem = (size_t)fft_size * sizeof(float2);
+        const size_t smem = fft_smem_bytes(fft_size);
         cudaFuncSetAttribute(istft_frames_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(n_frames, n_signals);
         istft_frames_kernel<double2><<<grid, fft_threads(fft_size), smem>>>(p);
@@ -382,7 +455,7 @@ int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int
     p.X = h->X;
     p.C = h->C;
     p.Tp = h->Tp;
-    const size_t smem = (size_t)fft_size * sizeof(float2);
+    const size_t smem = fft_smem_bytes(fft_size);
     BSS_CUDA(h, cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_frames, S);
     stft_kernel<<<grid, fft_threads(fft_size), smem, h->stream>>>(p);
@@ -418,7 +491,7 @@ int istft_from_device(bss_handle* h, const cf* z, int n_signals, int fft_size, i
     p.n_frames = n_frames;
     p.scale = (float)(t.win_sum / (double)(fft_size / 2));
     p.frames = frames;
-    const size_t smem = (size_t)fft_size * sizeof(float2);
+    const size_t smem = fft_smem_bytes(fft_size);
     BSS_CUDA(h, cudaFuncSetAttribute(istft_frames_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_frames, n_signals);
     istft_frames_kernel<float2><<<grid, fft_threads(fft_size), smem, h->stream>>>(p);
