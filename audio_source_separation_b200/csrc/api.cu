@@ -187,6 +187,8 @@ void bss_destroy(bss_handle* h) {
         if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+    if (h->graph_rec_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_rec_exec);
+    if (h->loss_counter) cudaFree(h->loss_counter);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -349,38 +351,58 @@ static uint64_t graph_signature(const bss_handle* h) {
     return s ? s : 1;
 }
 
-int bss_run(bss_handle* h, int n_iter) {
-    if (!h || n_iter < 0) return BSS_EINVAL;
-    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
-    if (is_nmf(h->cfg.method)) return nmf_run(h, n_iter, nullptr);   // one cluster launch for the whole loop when it fits
+// one loss evaluation queued on the stream; result at lossbuf[B*F .. B*F+B)
+static int loss_device(bss_handle* h) {
+    if (is_nmf(h->cfg.method)) return nmf_loss(h);
+    if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
+    if (h->cfg.method == BSS_IS_MNMF) return smnmf_loss(h);
+    return h->cfg.method == BSS_FAST_MNMF ? mnmf_loss(h) : bss_loss_device(h);
+}
+
+// n iterations, each optionally followed by the loss and its append to the device-side history
+static int run_eager_rec(bss_handle* h, int n_iter, bool record) {
+    if (!record) return run_eager(h, n_iter);
+    for (int i = 0; i < n_iter; ++i) {
+        BSS_TRY(run_eager(h, 1));
+        BSS_TRY(loss_device(h));
+        BSS_TRY(launch_loss_append(h, h->lossbuf + (size_t)h->B * h->F, h->loss_hist, h->loss_counter, h->B,
+                                   (int)(h->loss_hist_elems / (size_t)h->B)));
+    }
+    return BSS_OK;
+}
+
+static int run_loop(bss_handle* h, int n_iter, bool record) {
     const int kPerGraph = 2, kWarm = 2, kMinReplays = 4;
-    if (n_iter < kWarm + kPerGraph * kMinReplays || !graph_capable(h)) return run_eager(h, n_iter);
+    if (n_iter < kWarm + kPerGraph * kMinReplays || !graph_capable(h)) return run_eager_rec(h, n_iter, record);
     // eager warm-up: every scratch buffer reaches its final size and every kernel attribute is set before the capture
-    BSS_TRY(run_eager(h, kWarm));
+    BSS_TRY(run_eager_rec(h, kWarm, record));
     n_iter -= kWarm;
     // A handle that is used for job after job (batch.py keeps its handles) replays the graph it already has as long as
     // the captured kernel arguments still describe the current state: instantiating and destroying an executable graph
     // per call costs host time and synchronises with the other handles' streams, which serialised the pipelined
     // end-to-end job (profiles/r5b_e2e_timeline.txt).
+    void*& slot_exec = record ? h->graph_rec_exec : h->graph_exec;
+    uint64_t& slot_sig = record ? h->graph_rec_sig : h->graph_sig;
+    int64_t& slot_launches = record ? h->graph_rec_launches : h->graph_launches;
     const uint64_t sig = graph_signature(h);
     cudaGraphExec_t exec = nullptr;
     int64_t per_graph = 0;
-    if (h->graph_exec && sig != 0 && sig == h->graph_sig) {
-        exec = (cudaGraphExec_t)h->graph_exec;
-        per_graph = h->graph_launches;
+    if (slot_exec && sig != 0 && sig == slot_sig) {
+        exec = (cudaGraphExec_t)slot_exec;
+        per_graph = slot_launches;
     } else {
-        if (h->graph_exec) {
-            cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
-            h->graph_exec = nullptr;
-            h->graph_sig = 0;
+        if (slot_exec) {
+            cudaGraphExecDestroy((cudaGraphExec_t)slot_exec);
+            slot_exec = nullptr;
+            slot_sig = 0;
         }
         cudaGraph_t graph = nullptr;
         const int64_t l0 = h->launches;
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
-            return run_eager(h, n_iter);
+            return run_eager_rec(h, n_iter, record);
         }
-        const int rc_cap = run_eager(h, kPerGraph);
+        const int rc_cap = run_eager_rec(h, kPerGraph, record);
         const cudaError_t e_end = cudaStreamEndCapture(h->stream, &graph);
         per_graph = h->launches - l0;
         h->launches = l0;   // nothing of the capture has executed
@@ -388,27 +410,26 @@ int bss_run(bss_handle* h, int n_iter) {
             cudaGetLastError();
             if (graph) cudaGraphDestroy(graph);
             if (rc_cap != BSS_OK) return rc_cap;
-            return run_eager(h, n_iter);
+            return run_eager_rec(h, n_iter, record);
         }
         cudaGraphDestroy(graph);
-        h->graph_exec = exec;
-        h->graph_launches = per_graph;
+        slot_exec = exec;
+        slot_launches = per_graph;
         // the capture itself may have grown a scratch buffer: sign the state the kernels were actually recorded with
-        h->graph_sig = graph_signature(h) == sig ? sig : 0;
+        slot_sig = graph_signature(h) == sig ? sig : 0;
     }
     const int reps = n_iter / kPerGraph;
     for (int r = 0; r < reps; ++r) BSS_CUDA(h, cudaGraphLaunch(exec, h->stream));
     h->launches += per_graph * reps;
     h->graph_replays += reps;
-    return run_eager(h, n_iter - reps * kPerGraph);
+    return run_eager_rec(h, n_iter - reps * kPerGraph, record);
 }
 
-// one loss evaluation queued on the stream; result at lossbuf[B*F .. B*F+B)
-static int loss_device(bss_handle* h) {
-    if (is_nmf(h->cfg.method)) return nmf_loss(h);
-    if (!h->has_input) return bss_fail(h, BSS_ESTATE, "Specify data!");
-    if (h->cfg.method == BSS_IS_MNMF) return smnmf_loss(h);
-    return h->cfg.method == BSS_FAST_MNMF ? mnmf_loss(h) : bss_loss_device(h);
+int bss_run(bss_handle* h, int n_iter) {
+    if (!h || n_iter < 0) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (is_nmf(h->cfg.method)) return nmf_run(h, n_iter, nullptr);   // one cluster launch for the whole loop when it fits
+    return run_loop(h, n_iter, false);
 }
 
 int bss_run_record(bss_handle* h, int n_iter, double* loss) {
@@ -428,12 +449,12 @@ int bss_run_record(bss_handle* h, int n_iter, double* loss) {
             BSS_CUDA(h, cudaMemcpyAsync(loss, h->loss_hist, sizeof(double) * h->B * n_iter, cudaMemcpyDeviceToHost, h->stream));
         return check_flags(h);
     }
-    for (int i = 0; i < n_iter; ++i) {
-        BSS_TRY(bss_run(h, 1));
-        BSS_TRY(loss_device(h));
-        BSS_CUDA(h, cudaMemcpyAsync(h->loss_hist + (size_t)i * h->B, h->lossbuf + (size_t)h->B * h->F, sizeof(double) * h->B,
-                                    cudaMemcpyDeviceToDevice, h->stream));
-    }
+    // every iteration is followed by its loss, appended to the history at a device-side counter: the (update, loss, append)
+    // triples replay from a CUDA graph like the plain loop, so the default recordable_loss=True path of the reference
+    // (src/bss/ilrma.py:239-241) costs the loss kernels and nothing else
+    if (!h->loss_counter) BSS_CUDA(h, cudaMalloc((void**)&h->loss_counter, sizeof(int)));
+    BSS_CUDA(h, cudaMemsetAsync(h->loss_counter, 0, sizeof(int), h->stream));
+    BSS_TRY(run_loop(h, n_iter, true));
     if (n_iter > 0)
         BSS_CUDA(h, cudaMemcpyAsync(loss, h->loss_hist, sizeof(double) * h->B * n_iter, cudaMemcpyDeviceToHost, h->stream));
     return check_flags(h);
@@ -513,12 +534,12 @@ int bss_set_option(bss_handle* h, int option, int value) {
     switch (option) {
         case BSS_OPT_IP_KERNEL:
             if (value < 0 || value > 3) return bss_fail(h, BSS_EINVAL, "BSS_OPT_IP_KERNEL takes 0 (auto), 1, 2 or 3");
-            if (value != h->opt_ip_kernel) h->graph_sig = 0;   // a kept graph recorded the other kernel
+            if (value != h->opt_ip_kernel) h->graph_sig = h->graph_rec_sig = 0;   // a kept graph recorded the other kernel
             h->opt_ip_kernel = value;
             return BSS_OK;
         case BSS_OPT_SOURCE_MODEL:
             if (value < 0 || value > 2) return bss_fail(h, BSS_EINVAL, "BSS_OPT_SOURCE_MODEL takes 0 (auto), 1 or 2");
-            if (value != h->opt_source_model) h->graph_sig = 0;
+            if (value != h->opt_source_model) h->graph_sig = h->graph_rec_sig = 0;
             h->opt_source_model = value;
             return BSS_OK;
         case BSS_OPT_BLOCKING_SYNC:
@@ -526,7 +547,7 @@ int bss_set_option(bss_handle* h, int option, int value) {
             return BSS_OK;
         case BSS_OPT_ACT_CHUNKS:
             if (value < 0) return bss_fail(h, BSS_EINVAL, "BSS_OPT_ACT_CHUNKS takes 0 (auto) or a positive count");
-            if (value != h->opt_act_chunks) h->graph_sig = 0;
+            if (value != h->opt_act_chunks) h->graph_sig = h->graph_rec_sig = 0;
             h->opt_act_chunks = value;
             return BSS_OK;
     }

@@ -26,6 +26,10 @@ struct bss_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    void* graph_rec_exec = nullptr;   // same for bss_run_record: two x (update_once, loss, append to the device-side history)
+    uint64_t graph_rec_sig = 0;
+    int64_t graph_rec_launches = 0;
+    int* loss_counter = nullptr;   // device-side write position of the loss history
     void* graph_exec = nullptr;    // cudaGraphExec_t of the last captured pair of iterations (bss_run)
     uint64_t graph_sig = 0;        // signature of every device pointer the captured kernels were given (0: do not reuse)
     int64_t graph_launches = 0;    // kernel launches per replay of graph_exec
@@ -312,6 +316,7 @@ int launch_separate(bss_handle* h, const cf* X, const cf* Wf, const double2* sca
 int launch_export_y(bss_handle* h, const cf* Y, const double2* scale, cf* out, int B, int N, int F, int T, int Tp);
 int launch_ilrma_loss(bss_handle* h, const MuArgs& a, float expo, double* terms);
 int launch_loss_finish(bss_handle* h, const double* terms, const double* logdet, double coef, int B, int F, double* out);
+int launch_loss_append(bss_handle* h, const double* result, double* hist, int* counter, int B, int capacity);
 int launch_import_x(bss_handle* h, const void* staged, int dtype, cf* X, int B, int C, int F, int T, int Tp);
 int launch_frame_weights(bss_handle* h, const cf* src, const cf* Wf, int from_y, float* winv, float* raw, int B, int C, int F,
                          int T, int Tp, int kind, float eps);

@@ -535,6 +535,23 @@ int launch_ilrma_loss(bss_handle* h, const MuArgs& a, float expo, double* terms)
     return rc;
 }
 
+// hist[counter][b] = result[b]; ++counter -- the destination of a recorded loss lives in device memory so that the same launch
+// can be replayed from a CUDA graph for every iteration (bss_run_record)
+__global__ void loss_append_kernel(const double* result, double* hist, int* counter, int B, int capacity) {
+    const int i = *counter;
+    if (i < capacity && (int)threadIdx.x < B) hist[(size_t)i * B + threadIdx.x] = result[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = i + 1;
+}
+
+int launch_loss_append(bss_handle* h, const double* result, double* hist, int* counter, int B, int capacity) {
+    if (B > 1024) return bss_fail(h, BSS_EINVAL, "loss history: at most 1024 mixtures per handle");
+    loss_append_kernel<<<1, ((B + 31) / 32) * 32, 0, h->stream>>>(result, hist, counter, B, capacity);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
+    return BSS_OK;
+}
+
 int launch_loss_finish(bss_handle* h, const double* terms, const double* logdet, double coef, int B, int F, double* out) {
     loss_finish_kernel<<<B, 256, 0, h->stream>>>(terms, logdet, coef, F, out);
     h->launches++;
