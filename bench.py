@@ -530,6 +530,7 @@ def run_gpu_arm(args):
     value = world * B * steps / (ms * 1e-3)
     ip_kernel = h.get_info(_lib.INFO_IP_KERNEL)
     act_chunks = h.get_info(_lib.INFO_ACT_CHUNKS)
+    source_model = h.get_info(_lib.INFO_SOURCE_MODEL)   # 2: fused single-pass source model, 1: three passes
 
     # ---- parity of the timed state -------------------------------------------------------------------
     # (a) mixture 0 of the batch against a single-mixture handle that replays the same calls on the same kernels and the
@@ -559,6 +560,7 @@ def run_gpu_arm(args):
                                               "bit_identical": bool(np.array_equal(Wb[0], Ws[0]) and np.array_equal(Tb[0], Ts[0])
                                                                     and np.array_equal(Vb[0], Vs[0]))},
                   "ip_kernel": {1: "ip_sweep_kernel (thread per bin)", 2: "ip_sweep_group_kernel", 3: "fused in cov_kernel"}.get(ip_kernel, ip_kernel),
+                  "source_model": "fused single pass (mu_fused_kernel)" if source_model == _lib.SOURCE_MODEL_FUSED else "three passes",
                   "act_chunks": act_chunks, "state_before": (Wb[0], Tb[0], Vb[0])}
     h.update_once()          # one more (untimed) iteration on every rank: keeps the ranks in step, feeds check (b)
     if rank == 0:
@@ -571,7 +573,8 @@ def run_gpu_arm(args):
     cov_bytes = B * (8 * C * F * T + 8 * C * F * C * C + 4 * C * K_BASIS * (F + T))
     peak, peak_src = measured_hbm_peak()
     achieved = cov_bytes / (cov_ms * 1e-3) / 1e9
-    step_bytes = B * (3 * 8 * C * F * T)
+    passes = 2 if source_model == _lib.SOURCE_MODEL_FUSED else 3
+    step_bytes = B * (passes * 8 * C * F * T)
     traffic = None   # DRAM bytes of one launch from the committed ncu --set full capture (same workload only)
     try:
         with open(os.path.join(ROOT, 'profiles', 'cov_kernel_traffic.json')) as fh:
@@ -757,7 +760,9 @@ def run_gpu_arm(args):
                          "peak_source": peak_src},
             "roofline_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / steps * 1e-3) / 1e9, "unit": "GB/s",
                               "frac": step_bytes / (ms / steps * 1e-3) / 1e9 / peak,
-                              "note": "3 passes over X per iteration (basis MU, activation MU, covariance)"},
+                              "passes_over_X": passes,
+                              "note": ("2 passes over X per iteration (fused basis + activation update, covariance)" if passes == 2 else
+                                       "3 passes over X per iteration (basis MU, activation MU, covariance)")},
             "parity": parity,
             "cpu_baseline": cpu,
             "configs": cfgs,
