@@ -21,7 +21,7 @@ SPATIAL_IP, SPATIAL_ISS, SPATIAL_IP2 = 0, 1, 2
 NORMALIZE_NONE, NORMALIZE_POWER, NORMALIZE_PROJECTION_BACK = 0, 1, 2
 ALG_MM, ALG_ME, ALG_NAIVE, ALG_MM_FAST = 0, 1, 2, 3
 # enum bss_dtype
-F32, F64, C64, C128, I32 = 0, 1, 2, 3, 4
+F32, F64, C64, C128, I32, I16 = 0, 1, 2, 3, 4, 5
 # enum bss_state
 (STATE_DEMIX_FILTER, STATE_ESTIMATION, STATE_BASIS, STATE_ACTIVATION, STATE_LATENT, STATE_DIAGONALIZER,
  STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE, STATE_VARIANCE, STATE_ORDER, STATE_EIGVAL) = range(13)
@@ -32,7 +32,7 @@ IP_AUTO, IP_THREAD_PER_BIN, IP_LANE_GROUP, IP_FUSED, IP_PAIRWISE = 0, 1, 2, 3, 4
 INFO_IP_KERNEL, INFO_GRAPH_REPLAYS, INFO_LAUNCHES, INFO_ACT_CHUNKS, INFO_SOURCE_MODEL = 0, 1, 2, 3, 4
 
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64,
-           np.dtype(np.complex128): C128, np.dtype(np.int32): I32}
+           np.dtype(np.complex128): C128, np.dtype(np.int32): I32, np.dtype(np.int16): I16}
 
 
 class Config(ctypes.Structure):
@@ -192,7 +192,7 @@ class Handle:
 
     def set_input_waveform(self, x, fft_size, hop_size, window):
         """x (B,C,n_samples) float32/float64 on the host; the STFT runs on the device."""
-        x = as_host(x, np.float32 if x.dtype == np.float32 else np.float64)
+        x = as_host(x, x.dtype if x.dtype in (np.float32, np.int16) else np.float64)   # int16: PCM samples, scaled by 1 / 32768
         window = as_host(window, np.float64)
         self._check(self._lib.bss_set_input_waveform(self._h, _ptr(x), _DTYPES[x.dtype], x.shape[-1], int(fft_size), int(hop_size),
                                                      _ptr(window)))

@@ -79,10 +79,11 @@ class BatchedGaussILRMA:
         B, C, F, T = X.shape
         return h.separate((B, C, F, T), dtype, projection_back=True)
 
-    def _pipelined(self, B, C, F, T, iteration, basis, activation, pipeline, feed, drain):
+    def _pipelined(self, B, C, F, T, iteration, basis, activation, pipeline, feed, drain, on_done=None):
         """Run `feed(h, lo, hi)` -> `iteration` updates -> `drain(h, lo, hi)` for every sub-batch [lo, hi) of a batch of B
         mixtures, each sub-batch on its own handle, CUDA stream and host thread, so that the copies of one sub-batch overlap
-        the update loop of the others.  `pipeline`: a count, a list of sub-batch sizes, or 'ramp' (`ramp_sizes(B)`)."""
+        the update loop of the others.  `pipeline`: a count, a list of sub-batch sizes, or 'ramp' (`ramp_sizes(B)`).
+        `on_done(lo, hi)` is called on the calling thread for every sub-batch, in index order, as soon as it has drained."""
         from concurrent.futures import ThreadPoolExecutor
         K = self.n_basis
         if basis is None:
@@ -146,9 +147,15 @@ class BatchedGaussILRMA:
 
         if n_parts == 1:
             job(0)
+            if on_done is not None:
+                on_done(*spans[0])
         else:
             with ThreadPoolExecutor(max_workers=n_parts) as pool:
-                list(pool.map(job, range(n_parts)))
+                futures = [pool.submit(job, i) for i in range(n_parts)]
+                for i, fut in enumerate(futures):
+                    fut.result()
+                    if on_done is not None:
+                        on_done(*spans[i])
 
     def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline='ramp', device_out=None):
         """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
@@ -183,17 +190,19 @@ class BatchedGaussILRMA:
         return out if device_out is None else None
 
     def separate_waveform_batch(self, x, fft_size, hop_size=None, window_fn='hann', out=None, iteration=100, basis=None,
-                                activation=None, pipeline='ramp', device_out=None, loss_out=None):
+                                activation=None, pipeline='ramp', device_out=None, loss_out=None, on_done=None):
         """The whole job in the time domain, pipelined like `separate_batch`: x (B,C,n_samples) float32/float64 in host
         memory -> separated signals (B,N,n_out) of the same dtype written to `out` (allocated when None), n_out = the length
-        scipy.signal.istft returns.  STFT (src/transform/stft.py:4-8), update loop, projection back and ISTFT (:10-17) run on
+        scipy.signal.istft returns.  x may also be int16 PCM (a quarter of the bytes of the spectrograms): the samples are
+        scaled by 1 / 32768 on the device, as the reference's notebooks do after reading a wav file, and the output is float32.  STFT (src/transform/stft.py:4-8), update loop, projection back and ISTFT (:10-17) run on
         the device, so only waveforms cross PCIe: half the bytes of the spectrograms at 50 % overlap.
         `device_out`: address of a device buffer (B,N,n_out) of x's dtype on this model's GPU: the separated signals are left
         there instead of being copied to the host (None is returned).  `loss_out`: a float64 array (B,) that receives the
         final negative log-likelihood of every mixture (one small device-to-host read per sub-batch)."""
         from scipy import signal as ss
-        if x.dtype not in (np.float32, np.float64) or not x.flags.c_contiguous:
+        if x.dtype not in (np.float32, np.float64, np.int16) or not x.flags.c_contiguous:
             x = np.ascontiguousarray(x, dtype=np.float64)
+        out_dtype = np.dtype(np.float32) if x.dtype == np.int16 else x.dtype
         B, C, n_samples = x.shape
         if hop_size is None:
             hop_size = fft_size // 2
@@ -203,16 +212,17 @@ class BatchedGaussILRMA:
         _check_presets(B, C, F, T, self.n_basis, None, basis, activation)
         if device_out is None:
             if out is None:
-                out = np.empty((B, C, n_out), dtype=x.dtype)
-            if not (out.shape == (B, C, n_out) and out.dtype == x.dtype and out.flags.c_contiguous):
-                raise ValueError("out must be a C-contiguous {} array of shape {}".format(x.dtype, (B, C, n_out)))
+                out = np.empty((B, C, n_out), dtype=out_dtype)
+            if not (out.shape == (B, C, n_out) and out.dtype == out_dtype and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous {} array of shape {}".format(out_dtype, (B, C, n_out)))
         if loss_out is not None and not (loss_out.shape == (B,) and loss_out.dtype == np.float64):
             raise ValueError("loss_out must be a float64 array of shape {}".format((B,)))
-        dtype = _lib.F32 if x.dtype == np.float32 else _lib.F64
-        esz = x.dtype.itemsize
+        in_dtype = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.int16): _lib.I16}[x.dtype]
+        dtype = _lib.F32 if out_dtype == np.float32 else _lib.F64
+        esz = out_dtype.itemsize
 
         def feed(h, lo, hi):
-            h.set_input_waveform_ptr(x[lo:hi].ctypes.data, dtype, n_samples, fft_size, hop_size, window)
+            h.set_input_waveform_ptr(x[lo:hi].ctypes.data, in_dtype, n_samples, fft_size, hop_size, window)
 
         def drain(h, lo, hi):
             if device_out is not None:
@@ -224,7 +234,7 @@ class BatchedGaussILRMA:
             if loss_out is not None:
                 loss_out[lo:hi] = h.loss()   # waits for the stream: everything queued above is complete afterwards
 
-        self._pipelined(B, C, F, T, iteration, basis, activation, pipeline, feed, drain)
+        self._pipelined(B, C, F, T, iteration, basis, activation, pipeline, feed, drain, on_done=on_done)
         return out if device_out is None else None
 
     def separate_waveform_batch_sharded(self, x, fft_size, hop_size=None, window_fn='hann', iteration=100, basis=None, activation=None,
@@ -248,86 +258,38 @@ class BatchedGaussILRMA:
         T = _lib.stft_frames(n_samples, fft_size, hop_size)
         n_out = _lib.istft_length(T, fft_size, hop_size)
         xl = x[lo:hi]
-        tdtype = torch.float32 if xl.dtype == np.float32 else torch.float64
-        y_local = torch.empty((hi - lo, C, n_out), dtype=tdtype, device=torch.device('cuda', self.device))
-        if hi > lo:
-            self.separate_waveform_batch(xl, fft_size, hop_size, window_fn, iteration=iteration,
-                                         basis=None if basis is None else basis[lo:hi],
-                                         activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
-                                         device_out=y_local.data_ptr(), loss_out=loss_out)
-        if world == 1:
-            return y_local
-        sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
-        return gather_outputs(y_local, world, group=group, sizes=sizes)
-
-    def separate_batch_sharded(self, X, iteration=100, basis=None, activation=None, group=None, pipeline='ramp', local_only=False):
-        """The multi-GPU whole job (one process per GPU, torch.distributed initialised by the caller): every rank passes the
-        SAME global batch description -- X (B,C,F,T) in host memory, of which it only reads its own contiguous shard
-        `shard_range(B, rank, world)` -- runs its mixtures with `separate_batch` (copies pipelined against the update loop),
-        leaves the estimates on its GPU and takes part in the one collective of the path, the NCCL all-gather of the
-        separated outputs.  Returns a torch tensor (B,N,F,T) complex64 on this rank's GPU holding the estimates of ALL
-        mixtures in batch order (`local_only=True`: only this rank's shard, no collective).  `basis` / `activation` are
-        global (B,...) presets; when None every rank draws its own shard from NumPy's global state."""
-        import torch
-        import torch.distributed as dist
-        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        rank = dist.get_rank(group) if world > 1 else 0
-        B, C, F, T = X.shape
-        lo, hi = shard_range(B, rank, world)
-        _check_presets(B, C, F, T, self.n_basis, None, basis, activation)
+        tdtype = torch.float64 if xl.dtype == np.float64 else torch.float32
         device = torch.device('cuda', self.device)
-        y_local = torch.empty((hi - lo, C, F, T), dtype=torch.complex64, device=device)
-        if hi > lo:
-            self.separate_batch(X[lo:hi], iteration=iteration, basis=None if basis is None else basis[lo:hi],
-                                activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
-                                device_out=y_local.data_ptr())
-        if local_only or world == 1:
-            return y_local
         sizes = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
-        return torch.view_as_complex(gather_outputs(torch.view_as_real(y_local), world, group=group, sizes=sizes))
+        even = world > 1 and len(set(sizes)) == 1
+        if world == 1 or not even:
+            y_local = torch.empty((hi - lo, C, n_out), dtype=tdtype, device=device)
+            if hi > lo:
+                self.separate_waveform_batch(xl, fft_size, hop_size, window_fn, iteration=iteration,
+                                             basis=None if basis is None else basis[lo:hi],
+                                             activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
+                                             device_out=y_local.data_ptr(), loss_out=loss_out)
+            if world == 1:
+                return y_local
+            return gather_outputs(y_local, world, group=group, sizes=sizes)
+        # equal shards: every rank cuts its shard into the same sub-batches, and the outputs of sub-batch i are gathered (into
+        # their final places, batch order) as soon as every rank has finished it -- the collective overlaps the update loops
+        # of the later sub-batches; only the gather of the last, small sub-batch is exposed.  NCCL calls are issued from this
+        # thread in sub-batch order on every rank.
+        Bl = hi - lo
+        y_all = torch.empty((B, C, n_out), dtype=tdtype, device=device)
+        y_local = y_all[lo:hi]
 
-    def separate_waveforms(self, x, fft_size, hop_size=None, window_fn='hann', iteration=100, basis=None, activation=None,
-                           dtype=np.float64):
-        """Time domain in, time domain out: x (B,C,n_samples) real -> separated signals (B,N,n_out), n_out = the length
-        scipy.signal.istft returns (>= n_samples).  STFT, update loop and ISTFT all run on the device: only waveforms cross
-        PCIe (half the bytes of the spectrograms at 50 % overlap)."""
-        from scipy import signal as ss
-        x = np.ascontiguousarray(x, dtype=np.float32 if x.dtype == np.float32 else np.float64)
-        B, C, n_samples = x.shape
-        if hop_size is None:
-            hop_size = fft_size // 2
-        window = np.asarray(ss.get_window(window_fn, fft_size), dtype=np.float64)
-        F, T = fft_size // 2 + 1, _lib.stft_frames(n_samples, fft_size, hop_size)
-        K = self.n_basis
-        _check_presets(B, C, F, T, K, None, basis, activation)
-        h = self.open(B, C, F, T)
-        h.reset_spatial()
-        h.set_state(_lib.STATE_BASIS, np.random.rand(B, C, F, K) if basis is None else basis, np.float64)
-        h.set_state(_lib.STATE_ACTIVATION, np.random.rand(B, C, K, T) if activation is None else activation, np.float64)
-        h.set_input_waveform(x, fft_size, hop_size, window)
-        h.run(iteration)
-        return h.separate_waveform((B, C), fft_size, hop_size, window, dtype=dtype, projection_back=True)
+        def gather_part(plo, phi):
+            views = [y_all[r * Bl + plo:r * Bl + phi] for r in range(world)]
+            dist.all_gather(views, y_local[plo:phi], group=group)
 
-    def update_once(self):
-        self.handle.update_once()
-
-    def compute_negative_loglikelihood(self):
-        return self.handle.loss()
-
-    @property
-    def demix_filter(self):
-        B, C, F, T = self.shape
-        return self.handle.get_state(_lib.STATE_DEMIX_FILTER, (B, F, C, C), np.complex128)
-
-    @property
-    def basis(self):
-        B, C, F, T = self.shape
-        return self.handle.get_state(_lib.STATE_BASIS, (B, C, F, self.n_basis), np.float64)
-
-    @property
-    def activation(self):
-        B, C, F, T = self.shape
-        return self.handle.get_state(_lib.STATE_ACTIVATION, (B, C, self.n_basis, T), np.float64)
+        self.separate_waveform_batch(xl, fft_size, hop_size, window_fn, iteration=iteration,
+                                     basis=None if basis is None else basis[lo:hi],
+                                     activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
+                                     device_out=y_local.data_ptr(), loss_out=loss_out if loss_out is not None else np.zeros(Bl),
+                                     on_done=gather_part)
+        return y_all
 
 
 def ramp_sizes(n_items):

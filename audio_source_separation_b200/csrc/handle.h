@@ -357,6 +357,7 @@ int launch_mnmf_basis(bss_handle* h);
 int launch_mnmf_act(bss_handle* h);
 int launch_mnmf_scm(bss_handle* h);
 int launch_mnmf_weights(bss_handle* h, int tiled);
+int launch_covariance8(bss_handle* h, bool* done);   // kernels_cov8.cu: FastMNMF, 8 channels, weights computed in the kernel
 int launch_covariance_mma(bss_handle* h, const cf* X, const float* iw_tiled, double* U, int B, int F, int C, int NW, int T, int Tp,
                           bool* done);
 int launch_mnmf_loss_terms(bss_handle* h);

@@ -217,6 +217,11 @@ __global__ void __launch_bounds__(256) to_float_kernel(const double* in, float* 
     if (i < n) out[i] = (float)in[i];
 }
 
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const short* in, float* out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i] * (1.0f / 32768.0f);
+}
+
 bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 struct FftTables {
@@ -420,7 +425,7 @@ static int handle_tables(bss_handle* h, const double* window, int N, FftTables* 
 // on the handle's stream; the caller (finish_input) waits before the host buffer is handed back.
 int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int fft_size, int hop_size, const double* window) {
     if (!pow2(fft_size) || fft_size < 8 || fft_size > 16384) return bss_fail(h, BSS_EUNSUPPORTED, "fft_size must be a power of two in [8, 16384]");
-    if (dtype != BSS_F32 && dtype != BSS_F64) return bss_fail(h, BSS_EINVAL, "waveforms are float32 or float64");
+    if (dtype != BSS_F32 && dtype != BSS_F64 && dtype != BSS_I16) return bss_fail(h, BSS_EINVAL, "waveforms are float32, float64 or int16 PCM");
     if (fft_size / 2 + 1 != h->F) return bss_fail(h, BSS_EINVAL, "n_bins of the handle must be fft_size / 2 + 1");
     const int n_frames = bss_stft_frames(n_samples, fft_size, hop_size);
     if (n_frames != h->T) return bss_fail(h, BSS_EINVAL, "n_frames of the handle does not match the waveform length");
@@ -428,11 +433,16 @@ int stft_into_handle(bss_handle* h, const void* x, int dtype, int n_samples, int
     if (handle_tables(h, window, fft_size, &t) != BSS_OK) return bss_fail(h, BSS_ENOMEM, "stft tables");
     const int S = h->B * h->C;
     const long long n = (long long)S * n_samples;
-    // staging: [float waveform | double waveform (float64 input only)]
-    BSS_TRY(ensure_staging(h, (size_t)n * sizeof(float) + (dtype == BSS_F64 ? (size_t)n * sizeof(double) : 0)));
+    // staging: [float waveform | the waveform as it came (float64 or int16 input only)]
+    BSS_TRY(ensure_staging(h, (size_t)n * sizeof(float) + (dtype == BSS_F64 ? (size_t)n * sizeof(double) : dtype == BSS_I16 ? (size_t)n * 2 : 0)));
     float* xf = (float*)h->staging;
     if (dtype == BSS_F32) {
         BSS_CUDA(h, cudaMemcpyAsync(xf, x, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else if (dtype == BSS_I16) {
+        short* staged = (short*)((char*)h->staging + (size_t)n * sizeof(float));
+        BSS_CUDA(h, cudaMemcpyAsync(staged, x, n * 2, cudaMemcpyHostToDevice, h->stream));
+        pcm16_to_float_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(staged, xf, n);
+        h->launches += 1;
     } else {
         double* staged = (double*)((char*)h->staging + (size_t)n * sizeof(float));
         BSS_CUDA(h, cudaMemcpyAsync(staged, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));

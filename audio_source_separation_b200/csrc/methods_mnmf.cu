@@ -73,10 +73,13 @@ int mnmf_update_once(bss_handle* h) {
     BSS_TRY(launch_mnmf_scm(h));
     // update_diagonalizer (:848-888): R is fixed during the sweep over channels, so all M weighted
     // covariances come from one pass and the Gauss-Seidel sweep runs per bin in registers
-    // all M weighted covariances of a bin as one tensor-core contraction (kernels_cov_mma.cu) ...
-    BSS_TRY(launch_mnmf_weights(h, 1));
-    bool on_tensor_cores = false;
-    BSS_TRY(launch_covariance_mma(h, h->X, h->iw, h->U, h->B, h->F, h->C, h->C, h->T, h->Tp, &on_tensor_cores));
+    // eight channels: one kernel, inverse variances computed on the fly, a lane per Hermitian entry (kernels_cov8.cu) ...
+    bool lane_per_entry = false;
+    BSS_TRY(launch_covariance8(h, &lane_per_entry));
+    // ... otherwise all M weighted covariances of a bin as one tensor-core contraction (kernels_cov_mma.cu) ...
+    bool on_tensor_cores = lane_per_entry;
+    if (!lane_per_entry) BSS_TRY(launch_mnmf_weights(h, 1));
+    if (!lane_per_entry) BSS_TRY(launch_covariance_mma(h, h->X, h->iw, h->U, h->B, h->F, h->C, h->C, h->T, h->Tp, &on_tensor_cores));
     // ... or, for shapes it does not cover, the CUDA-core kernel with explicit weights
     if (!on_tensor_cores) BSS_TRY(launch_mnmf_weights(h, 0));
     CovArgs c{};
@@ -126,6 +129,9 @@ int mnmf_loss(bss_handle* h) {
 // the covariance-accumulate step of update_diagonalizer alone (bss_time_covariance): inverse weights from (W, H, g), then
 // all M weighted covariances of every bin
 int mnmf_covariance_only(bss_handle* h) {
+    bool lane_per_entry = false;
+    BSS_TRY(launch_covariance8(h, &lane_per_entry));
+    if (lane_per_entry) return BSS_OK;
     BSS_TRY(launch_mnmf_weights(h, 1));
     bool on_tensor_cores = false;
     BSS_TRY(launch_covariance_mma(h, h->X, h->iw, h->U, h->B, h->F, h->C, h->C, h->T, h->Tp, &on_tensor_cores));

@@ -617,11 +617,13 @@ def run_gpu_arm(args):
     # (2) waveforms across PCIe: the time-domain signals whose STFT has the headline shape (white noise through a random
     #     mixing matrix: throughput input; the STFT feed has its own parity tests)
     n_samples = (T - 1) * HOP
-    wave_in = torch.empty((B, C, n_samples), dtype=torch.float32, pin_memory=True)
+    # 16-bit PCM, the format recordings come in (the reference's notebooks read int16 wav files and divide by 32768)
+    wave_in = torch.empty((B, C, n_samples), dtype=torch.int16, pin_memory=True)
     rng = np.random.default_rng(50_000 + rank)
     for b in range(B):
         src = rng.standard_normal((C, n_samples), dtype=np.float32) * rng.random((C, 1), dtype=np.float32)
-        wave_in.numpy()[b] = (np.eye(C, dtype=np.float32) + 0.4 * rng.standard_normal((C, C), dtype=np.float32)) @ src
+        mix = (np.eye(C, dtype=np.float32) + 0.4 * rng.standard_normal((C, C), dtype=np.float32)) @ src
+        wave_in.numpy()[b] = np.clip(mix * 4000.0, -32767, 32767).astype(np.int16)
     n_out = _lib.istft_length(T, FFT, HOP)
     wave_out = torch.empty((B, C, n_out), dtype=torch.float32, pin_memory=True)
     assert _lib.stft_frames(n_samples, FFT, HOP) == T
@@ -722,7 +724,7 @@ def run_gpu_arm(args):
         if parity is not None:
             parity.pop("state_before", None)
             parity.pop("state_after", None)
-        wave_h2d = wave_in.numel() * 4
+        wave_h2d = wave_in.numel() * 2
         wave_d2h = wave_out.numel() * 4
         line = {
             "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -735,9 +737,10 @@ def run_gpu_arm(args):
                        "l2": "inputs larger than L2 ({:.2f} GB per GPU per pass): no flush".format(B * 8 * C * F * T / 1e9),
                        "storage": "complex64/float32 tensors, float64 per-bin solves",
                        "e2e_job": "BASELINE configs[4] as one call, BatchedGaussILRMA.separate_waveform_batch_sharded (pipelined "
-                                  "sub-batches: {}): H2D of the rank's float32 waveforms ({} samples x 4ch per mixture) from pinned memory + "
+                                  "sub-batches: {}): H2D of the rank's int16 PCM waveforms ({} samples x 4ch per mixture) from pinned memory + "
                                   "STFT ({}/{}) + {} iterations + separate/projection-back + ISTFT on the device + NCCL all-gather of all "
-                                  "separated signals onto every GPU (N = 1: no collective, the signals stay on the GPU) + D2H of the "
+                                  "separated float32 signals onto every GPU, sub-batch by sub-batch behind the update loops of the later "
+                                  "ones (N = 1: no collective, the signals stay on the GPU) + D2H of the "
                                   "final per-mixture losses; bytes amortised per iteration.  e2e_host_* are the same job with the "
                                   "outputs delivered to pinned host memory instead (bound by the host link of the box, see "
                                   "profiles/r6d_pcie_probe_8gpu.json)".format(pipeline, n_samples, FFT, HOP, steps)},

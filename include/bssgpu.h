@@ -83,7 +83,8 @@ enum bss_nmf_algorithm {      /* `algorithm` of the NMF constructors */
     BSS_ALG_MM_FAST = 3       /* CauchyNMF 'mm_fast'              */
 };
 
-enum bss_dtype { BSS_F32 = 0, BSS_F64 = 1, BSS_C64 = 2, BSS_C128 = 3, BSS_I32 = 4 };
+enum bss_dtype { BSS_F32 = 0, BSS_F64 = 1, BSS_C64 = 2, BSS_C128 = 3, BSS_I32 = 4,
+                 BSS_I16 = 5 /* 16-bit PCM waveforms (bss_set_input_waveform): sample / 32768, as the reference's notebooks read wav files */ };
 
 /* State tensors (host layouts, leading B omitted):
  *   DEMIX_FILTER   (F,N,C) complex   model.demix_filter
@@ -178,7 +179,7 @@ int bss_synchronize(bss_handle* h);
  * Also precomputes the plain spatial covariance mean_t x x^H used by the algebraic forms of
  * power normalisation and projection back. */
 int bss_set_input(bss_handle* h, const void* x, int dtype);
-/* the same from the time-domain mixture: x is (B,C,n_samples) float32/float64 on the host; the STFT of
+/* the same from the time-domain mixture: x is (B,C,n_samples) float32/float64, or int16 PCM (scaled by 1/32768), on the host; the STFT of
  * src/transform/stft.py:4-8 (scipy.signal.stft: zero boundary extension, tail padding, `window`, onesided,
  * divided by sum(window)) is computed on the device straight into the bin tiles.  The handle must have
  * n_bins = fft_size/2 + 1 and n_frames = bss_stft_frames(n_samples, fft_size, hop_size); fft_size a power of two. */

@@ -133,3 +133,23 @@ def test_pipelined_waveform_job_equals_the_single_handle_call(cuda_device):
     assert got32.dtype == np.float32 and rel(got32, want) < 1e-4
     with pytest.raises(ValueError):
         model.separate_waveform_batch(x, fft, hop, iteration=1, basis=T0[:, :, :-1], activation=V0)
+
+
+def test_pcm16_waveform_feed(cuda_device):
+    """int16 PCM in (scaled by 1 / 32768 on the device, as the reference's notebooks do after wavfile.read) equals the float
+    feed of the same samples, through the single-handle and the pipelined job."""
+    from audio_source_separation_b200.batch import BatchedGaussILRMA
+    rng = np.random.default_rng(6)
+    B, C, K, n_samples, fft, hop = 4, 2, 2, 4000, 256, 64
+    pcm = rng.integers(-20000, 20000, size=(B, C, n_samples)).astype(np.int16)
+    xf = pcm.astype(np.float32) / 32768
+    F = fft // 2 + 1
+    T = len(ss.stft(xf[0, 0], nperseg=fft, noverlap=fft - hop)[1])
+    T0, V0 = rng.random((B, C, F, K)), rng.random((B, C, K, T))
+    want = BatchedGaussILRMA(n_basis=K).separate_waveform_batch(xf, fft, hop, iteration=5, basis=T0, activation=V0, pipeline=1)
+    got = BatchedGaussILRMA(n_basis=K).separate_waveform_batch(pcm, fft, hop, iteration=5, basis=T0, activation=V0, pipeline=2)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    loss = np.zeros(B)
+    BatchedGaussILRMA(n_basis=K).separate_waveform_batch(pcm, fft, hop, iteration=5, basis=T0, activation=V0, pipeline=2, loss_out=loss)
+    assert np.all(np.isfinite(loss)) and np.all(loss != 0)
