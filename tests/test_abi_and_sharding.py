@@ -179,3 +179,12 @@ def test_bench_reference_arm_line_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
                          capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_batched_public_surface_is_complete():
+    """The batch extension's public entry points (DESIGN.md section 6 / INTEGRATION.md): a refactoring once dropped some."""
+    from audio_source_separation_b200.batch import BatchedGaussILRMA, gather_outputs, ramp_sizes, shard_range  # noqa: F401
+    for name in ('open', 'reset', '__call__', 'separate_batch', 'separate_batch_sharded', 'separate_waveform_batch',
+                 'separate_waveform_batch_sharded', 'separate_waveforms', 'update_once', 'compute_negative_loglikelihood',
+                 'demix_filter', 'basis', 'activation'):
+        assert hasattr(BatchedGaussILRMA, name), name
