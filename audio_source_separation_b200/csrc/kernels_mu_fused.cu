@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, MINB) mu_fused_kernel(const
             tnew = told * sqrtf(nm / dn);
             if (warp == 0) a.basis_out[(((size_t)b * N + lane / KC) * a.F + f) * KC + (lane % KC)] = tnew;
         }
+        __syncwarp();   // the last read of the stage (tb) is behind every lane: lane 0 may refill it at the top of the next bin
         float tn[N][KC];
 #pragma unroll
         for (int n = 0; n < N; ++n)
