@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbssgpu.so')
 
 # enum bss_status
-OK, EINVAL, ECUDA, ESINGULAR, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+OK, EINVAL, ECUDA, ESINGULAR, ENOMEM, ESTATE, EUNSUPPORTED, ENCCL = 0, -1, -2, -3, -4, -5, -6, -7
 # enum bss_method
 GAUSS_ILRMA, T_ILRMA, AUX_LAPLACE_IVA, AUX_GAUSS_IVA, FAST_MNMF, IS_MNMF, GAUSS_IDLMA = 0, 1, 2, 3, 4, 5, 6
 NMF_EUC, NMF_KL, NMF_IS, NMF_T, NMF_CAUCHY = 10, 11, 12, 13, 14
@@ -73,6 +73,7 @@ SIGNATURES = {
     'bss_separate_device': (_i, [_vp, _vp, _i]),
     'bss_separate_waveform': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     'bss_separate_waveform_device': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    'bss_gather_outputs': (_i, [_vp, _vp, _i, _i, _vp, _vp, ctypes.c_size_t, ctypes.c_size_t]),
     'bss_compute_demix_filter': (_i, [_vp]),
     'bss_set_option': (_i, [_vp, _i, _i]),
     'bss_get_info': (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
@@ -119,6 +120,8 @@ def _raise(code, message):
         raise NotImplementedError(message)
     if code == ENOMEM:
         raise MemoryError(message)
+    if code == ENCCL:
+        raise RuntimeError("NCCL: {}".format(message))
     raise RuntimeError("libbssgpu error {}: {}".format(code, message))
 
 
@@ -277,6 +280,11 @@ class Handle:
     def compute_demix_filter(self):
         self._check(self._lib.bss_compute_demix_filter(self._h))
 
+    def gather_outputs(self, comm, send_ptr, recv_base_ptr, nbytes, rank_stride_bytes):
+        """All-gather on the handle's stream over `comm` (an `NcclComm`): rank r's `nbytes` land at recv_base + r * stride."""
+        self._check(self._lib.bss_gather_outputs(self._h, comm.handle, comm.world, comm.rank, ctypes.c_void_p(send_ptr),
+                                                 ctypes.c_void_p(recv_base_ptr), int(nbytes), int(rank_stride_bytes)))
+
     def set_option(self, option, value):
         self._check(self._lib.bss_set_option(self._h, int(option), int(value)))
 
@@ -301,6 +309,50 @@ class Handle:
 
     def launch_count(self):
         return int(self._lib.bss_launch_count(self._h))
+
+
+class NcclComm:
+    """An NCCL communicator of our own for `bss_gather_outputs` (one per process / GPU), created through the same
+    libnccl.so.2 the process already carries.  The 128-byte unique id travels through the caller's torch.distributed group
+    (any backend), which is only used for that."""
+
+    def __init__(self, rank, world, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world = int(rank), int(world)
+        self._nccl = None
+        for name in ('libnccl.so.2', 'libnccl.so'):
+            try:
+                self._nccl = ctypes.CDLL(name, mode=ctypes.RTLD_GLOBAL)
+                break
+            except OSError:
+                continue
+        if self._nccl is None:
+            raise RuntimeError("libnccl.so.2 not found")
+        uid = (ctypes.c_char * 128)()
+        if self.rank == 0:
+            rc = self._nccl.ncclGetUniqueId(ctypes.byref(uid))
+            if rc != 0:
+                raise RuntimeError("ncclGetUniqueId failed ({})".format(rc))
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        torch.cuda.set_device(device)
+        comm = ctypes.c_void_p()
+
+        class _Uid(ctypes.Structure):
+            _fields_ = [('internal', ctypes.c_char * 128)]
+        self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
+        rc = self._nccl.ncclCommInitRank(ctypes.byref(comm), self.world, _Uid(uid.raw), self.rank)
+        if rc != 0:
+            raise RuntimeError("ncclCommInitRank failed ({})".format(rc))
+        self.handle = comm
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self._nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self._nccl.ncclCommDestroy(self.handle)
+            self.handle = None
 
 
 # stateless primitives ---------------------------------------------------------------------------

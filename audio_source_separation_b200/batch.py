@@ -83,7 +83,8 @@ class BatchedGaussILRMA:
         """Run `feed(h, lo, hi)` -> `iteration` updates -> `drain(h, lo, hi)` for every sub-batch [lo, hi) of a batch of B
         mixtures, each sub-batch on its own handle, CUDA stream and host thread, so that the copies of one sub-batch overlap
         the update loop of the others.  `pipeline`: a count, a list of sub-batch sizes, or 'ramp' (`ramp_sizes(B)`).
-        `on_done(lo, hi)` is called on the calling thread for every sub-batch, in index order, as soon as it has drained."""
+        `on_done(i, lo, hi)` is called on the calling thread for every sub-batch, in index order, as soon as it has drained
+        (`self._parts[i][1]` is its handle)."""
         from concurrent.futures import ThreadPoolExecutor
         K = self.n_basis
         if basis is None:
@@ -148,14 +149,14 @@ class BatchedGaussILRMA:
         if n_parts == 1:
             job(0)
             if on_done is not None:
-                on_done(*spans[0])
+                on_done(0, *spans[0])
         else:
             with ThreadPoolExecutor(max_workers=n_parts) as pool:
                 futures = [pool.submit(job, i) for i in range(n_parts)]
                 for i, fut in enumerate(futures):
                     fut.result()
                     if on_done is not None:
-                        on_done(*spans[i])
+                        on_done(i, *spans[i])
 
     def separate_batch(self, X, out=None, iteration=100, basis=None, activation=None, pipeline='ramp', device_out=None):
         """Whole job for a batch held in host memory: X (B,C,F,T) complex64/128 -> projection-backed estimates written to
@@ -275,21 +276,57 @@ class BatchedGaussILRMA:
         # equal shards: every rank cuts its shard into the same sub-batches, and the outputs of sub-batch i are gathered (into
         # their final places, batch order) as soon as every rank has finished it -- the collective overlaps the update loops
         # of the later sub-batches; only the gather of the last, small sub-batch is exposed.  NCCL calls are issued from this
-        # thread in sub-batch order on every rank.
+        # thread in sub-batch order on every rank.  The collective is `bss_gather_outputs` (C ABI: one NCCL group of
+        # broadcasts on the sub-batch handle's own stream, straight into the final places) over a communicator of our own;
+        # torch.distributed's all_gather serves when that communicator cannot be created.
         Bl = hi - lo
         y_all = torch.empty((B, C, n_out), dtype=tdtype, device=device)
         y_local = y_all[lo:hi]
+        row_bytes = C * n_out * y_all.element_size()
+        comm = self._own_comm(rank, world, group)
+        self.gather_backend = 'bss_gather_outputs' if comm is not None else 'torch.distributed.all_gather'
 
-        def gather_part(plo, phi):
-            views = [y_all[r * Bl + plo:r * Bl + phi] for r in range(world)]
-            dist.all_gather(views, y_local[plo:phi], group=group)
+        def gather_part(i, plo, phi):
+            if comm is not None:
+                h = self._parts[i][1]
+                h.gather_outputs(comm, y_local[plo:phi].data_ptr(), y_all.data_ptr() + plo * row_bytes, (phi - plo) * row_bytes,
+                                 Bl * row_bytes)
+            else:
+                views = [y_all[r * Bl + plo:r * Bl + phi] for r in range(world)]
+                dist.all_gather(views, y_local[plo:phi], group=group)
 
         self.separate_waveform_batch(xl, fft_size, hop_size, window_fn, iteration=iteration,
                                      basis=None if basis is None else basis[lo:hi],
                                      activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
                                      device_out=y_local.data_ptr(), loss_out=loss_out if loss_out is not None else np.zeros(Bl),
                                      on_done=gather_part)
+        if comm is not None:
+            for slot in self._parts:    # the gathers were queued on the sub-batch streams
+                if slot is not None:
+                    slot[1].synchronize()
         return y_all
+
+    def _own_comm(self, rank, world, group):
+        """NCCL communicator for `bss_gather_outputs`, created once per model (None when NCCL cannot be set up that way; every
+        rank then agrees on the fallback through one small all-reduce)."""
+        import torch
+        import torch.distributed as dist
+        cached = getattr(self, '_comm', None)
+        if cached is not None and cached[0] == (rank, world):
+            return cached[1]
+        comm = None
+        try:
+            comm = _lib.NcclComm(rank, world, self.device, group=group)
+        except Exception:
+            comm = None
+        ok = torch.tensor([1 if comm is not None else 0], device=torch.device('cuda', self.device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if comm is not None:
+                comm.close()
+            comm = None
+        self._comm = ((rank, world), comm)
+        return comm
 
     def separate_batch_sharded(self, X, iteration=100, basis=None, activation=None, group=None, pipeline='ramp', local_only=False):
         """The multi-GPU whole job (one process per GPU, torch.distributed initialised by the caller): every rank passes the

@@ -5,10 +5,42 @@
 #include <cstring>
 #include <new>
 
+#include <dlfcn.h>
+
 #include "handle.h"
 #include "methods.h"
 
 static thread_local std::string g_create_error;
+
+// NCCL is resolved at run time: the library has no link-time dependency on it, and a process that already carries
+// libnccl.so.2 (torch does) shares that copy.
+namespace {
+typedef int (*nccl_group_fn)(void);
+typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_err_fn)(int);
+struct NcclApi {
+    nccl_group_fn group_start = nullptr, group_end = nullptr;
+    nccl_bcast_fn broadcast = nullptr;
+    nccl_err_fn error_string = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl_api() {
+    static const NcclApi api = [] {
+        NcclApi a;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return a;
+        a.group_start = (nccl_group_fn)dlsym(lib, "ncclGroupStart");
+        a.group_end = (nccl_group_fn)dlsym(lib, "ncclGroupEnd");
+        a.broadcast = (nccl_bcast_fn)dlsym(lib, "ncclBroadcast");
+        a.error_string = (nccl_err_fn)dlsym(lib, "ncclGetErrorString");
+        a.ok = a.group_start && a.group_end && a.broadcast;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
 
 namespace {
 
@@ -527,6 +559,26 @@ int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int f
     BSS_TRY(ensure_staging(h, elems * 8));
     BSS_TRY(bss_separate_device(h, h->staging, apply_projection_back));
     return istft_from_device(h, (const cf*)h->staging, h->B * h->N, fft_size, hop_size, window, y_device, dtype, 1);
+}
+
+int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, const void* send_device, void* recv_base_device,
+                       size_t bytes, size_t rank_stride_bytes) {
+    if (!h || !nccl_comm || !send_device || !recv_base_device || n_ranks < 1 || rank < 0 || rank >= n_ranks) return BSS_EINVAL;
+    const NcclApi& nccl = nccl_api();
+    if (!nccl.ok) return bss_fail(h, BSS_ENCCL, "libnccl.so.2 not found");
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (bytes == 0) return BSS_OK;
+    auto check = [&](int rc, const char* what) -> int {
+        if (rc == 0) return BSS_OK;
+        return bss_fail(h, BSS_ENCCL, std::string(what) + ": " + (nccl.error_string ? nccl.error_string(rc) : "NCCL error"));
+    };
+    BSS_TRY(check(nccl.group_start(), "ncclGroupStart"));
+    int rc = 0;
+    for (int r = 0; r < n_ranks && rc == 0; ++r)
+        rc = nccl.broadcast(send_device, (char*)recv_base_device + (size_t)r * rank_stride_bytes, bytes, /*ncclInt8*/ 0, r, nccl_comm, h->stream);
+    const int rc_end = nccl.group_end();
+    BSS_TRY(check(rc, "ncclBroadcast"));
+    return check(rc_end, "ncclGroupEnd");
 }
 
 int bss_set_option(bss_handle* h, int option, int value) {

@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(NT) nmf_fused_kernel(const NmfFusedParams p) {
                     den[k] = fma(s2, vk[k], den[k]);
                 }
             }
+            __syncwarp();   // every lane has read the old basis row (tk) before lane k overwrites element k
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const double a = warp_sum(num[k]);

@@ -45,7 +45,8 @@ enum bss_status {
     BSS_ESINGULAR = -3,    /* exactly singular bin: np.linalg.LinAlgError in the reference */
     BSS_ENOMEM = -4,
     BSS_ESTATE = -5,       /* call order violated (e.g. update before set_input)        */
-    BSS_EUNSUPPORTED = -6  /* NotImplementedError in the reference                      */
+    BSS_EUNSUPPORTED = -6, /* NotImplementedError in the reference                      */
+    BSS_ENCCL = -7         /* NCCL missing or a collective failed (RuntimeError)        */
 };
 
 enum bss_method {
@@ -234,6 +235,14 @@ int bss_get_info(bss_handle* h, int what, int64_t* value);
  * the handle's stream (bss_synchronize before another stream reads it) -- feeds the NCCL gather of a sharded batch */
 int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int fft_size, int hop_size, const double* window,
                                  int apply_projection_back);
+/* The one collective of a sharded batch (BASELINE configs[4]: "NVLink gather only at end"): every rank contributes `bytes`
+ * bytes at send_device and receives rank r's contribution at recv_base_device + r * rank_stride_bytes (r = 0 .. n_ranks-1,
+ * its own included), on the handle's stream, as one NCCL group of broadcasts -- so a sub-batch can be gathered straight into
+ * its final place of a (global batch, ...) buffer while later sub-batches are still iterating.  `nccl_comm` is an
+ * ncclComm_t of n_ranks ranks created by the caller (libnccl.so.2 is resolved at run time, the library does not link it).
+ * Every rank must call it in the same order.  No reference counterpart (the reference has no batch axis). */
+int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, const void* send_device, void* recv_base_device,
+                       size_t bytes, size_t rank_stride_bytes);
 /* ISS keeps no filter: W = Y X^H (X X^H)^-1 (src/bss/ilrma.py:167-173); result is readable as
  * BSS_STATE_DEMIX_FILTER afterwards */
 int bss_compute_demix_filter(bss_handle* h);
