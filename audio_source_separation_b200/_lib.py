@@ -329,21 +329,25 @@ class NcclComm:
                 continue
         if self._nccl is None:
             raise RuntimeError("libnccl.so.2 not found")
-        uid = (ctypes.c_char * 128)()
+        class _Uid(ctypes.Structure):      # ncclUniqueId { char internal[128]; }, passed BY VALUE to ncclCommInitRank
+            _fields_ = [('internal', ctypes.c_byte * 128)]
+        uid = _Uid()
         if self.rank == 0:
+            self._nccl.ncclGetUniqueId.argtypes = [ctypes.POINTER(_Uid)]
+            self._nccl.ncclGetUniqueId.restype = ctypes.c_int
             rc = self._nccl.ncclGetUniqueId(ctypes.byref(uid))
             if rc != 0:
                 raise RuntimeError("ncclGetUniqueId failed ({})".format(rc))
-        box = [bytes(uid.raw)]
+        box = [bytes(bytearray(uid.internal))]
         dist.broadcast_object_list(box, src=0, group=group)
-        uid = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        if len(box[0]) != 128:
+            raise RuntimeError("NCCL unique id did not arrive")
+        ctypes.memmove(ctypes.byref(uid), box[0], 128)
         torch.cuda.set_device(device)
         comm = ctypes.c_void_p()
-
-        class _Uid(ctypes.Structure):
-            _fields_ = [('internal', ctypes.c_char * 128)]
         self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
-        rc = self._nccl.ncclCommInitRank(ctypes.byref(comm), self.world, _Uid(uid.raw), self.rank)
+        self._nccl.ncclCommInitRank.restype = ctypes.c_int
+        rc = self._nccl.ncclCommInitRank(ctypes.byref(comm), self.world, uid, self.rank)
         if rc != 0:
             raise RuntimeError("ncclCommInitRank failed ({})".format(rc))
         self.handle = comm

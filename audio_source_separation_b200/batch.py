@@ -315,9 +315,11 @@ class BatchedGaussILRMA:
         if cached is not None and cached[0] == (rank, world):
             return cached[1]
         comm = None
+        self.gather_backend_error = None
         try:
             comm = _lib.NcclComm(rank, world, self.device, group=group)
-        except Exception:
+        except Exception as exc:   # reported through gather_backend / gather_backend_error; the torch collective serves
+            self.gather_backend_error = "{}: {}".format(type(exc).__name__, exc)
             comm = None
         ok = torch.tensor([1 if comm is not None else 0], device=torch.device('cuda', self.device))
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)

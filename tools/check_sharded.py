@@ -32,7 +32,8 @@ for pipeline in ([2, 3, 5], 1):
     ref = torch.empty((B, C, ref_local.shape[-1]), dtype=torch.float32, device='cuda')
     dist.all_gather_into_tensor(ref, torch.from_numpy(ref_local).cuda())
     same = bool(torch.equal(y_all, ref))
-    out[str(pipeline)] = {"equal": same, "backend": model.gather_backend, "max_abs_diff": float((y_all - ref).abs().max())}
+    out[str(pipeline)] = {"equal": same, "backend": model.gather_backend, "backend_error": getattr(model, 'gather_backend_error', None),
+                          "max_abs_diff": float((y_all - ref).abs().max())}
     assert np.all(np.isfinite(loss))
 flag = torch.tensor([1 if all(v["equal"] for v in out.values()) else 0], device='cuda')
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
