@@ -270,8 +270,7 @@ SM_HD void herm_unpack(const double* p, Mat<C>& U) {
 // w = A^-1 e_n and |det A|^2 by Gaussian elimination with partial pivoting of [A | e_n] (the pivoting rule of mat_inverse),
 // a third of the work of the full inverse.  Returns false on an exactly zero pivot.
 template <int C>
-SM_HD bool solve_unit(const Mat<C>& Ain, int n, cd (&w)[C], double* absdet2) {
-    Mat<C> A = Ain;
+SM_HD bool solve_unit_inplace(Mat<C>& A, int n, cd (&w)[C], double* absdet2) {   // A is overwritten by the elimination
     cd b[C], rp[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) b[i] = cd_make(i == n ? 1.0 : 0.0, 0.0);
@@ -326,10 +325,44 @@ SM_HD bool solve_unit(const Mat<C>& Ain, int n, cd (&w)[C], double* absdet2) {
 }
 
 template <int C>
-SM_HD int ip_row(Mat<C>& W, const Mat<C>& U, int n, double threshold, bool use_gate, bool floor_den, double eps,
-                 bool* singular) {
-    Mat<C> A;
-    mat_mul(W, U, A);
+SM_HD bool solve_unit(const Mat<C>& Ain, int n, cd (&w)[C], double* absdet2) {
+    Mat<C> A = Ain;
+    return solve_unit_inplace(A, n, w, absdet2);
+}
+
+// The exact route of a row update: full inverse, gate decision from cond_2 (Frobenius bounds, Jacobi SVD in the undecided
+// band), w = column n of the inverse.  Rare (ill-conditioned, near-threshold, singular or non-finite bins only), so it is kept
+// out of line: inlined, its two extra matrices pushed the common path of the thread-per-bin kernel into local memory.
+// Returns 1 (update), 0 (kept by the gate) or -1 (exactly singular).
+#if defined(__CUDACC__)
+#define SM_NOINLINE __host__ __device__ __noinline__
+#else
+#define SM_NOINLINE inline
+#endif
+template <int C>
+SM_NOINLINE int ip_row_exact(const Mat<C>* Ap, int n, double threshold, bool use_gate, cd* w) {
+    const Mat<C>& A = *Ap;
+    Mat<C> Ainv;
+    const bool inv_ok = mat_inverse(A, Ainv);
+    if (!inv_ok) return -1;
+    const bool ok = use_gate ? cond_below(A, Ainv, inv_ok, threshold) : true;
+    // w = A^-1 e_n : column n of the inverse (compile-time indexed select)
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        w[i] = Ainv.a[i][0];
+#pragma unroll
+        for (int j = 1; j < C; ++j)
+            if (j == n) w[i] = Ainv.a[i][j];
+    }
+    return ok ? 1 : 0;
+}
+
+// The row update given a way to form A = W U (`make_A(A)`; called a second time only on the rare exact route, because the
+// elimination of the common route overwrites A in place -- a kept copy costs 64 registers): on return `row` holds the new
+// row n (conj(w) / sqrt(w^H U w)) when the result is 1.
+template <int C, class MakeA>
+SM_HD int ip_row_from_product(const MakeA& make_A, const Mat<C>& U, int n, double threshold, bool use_gate, bool floor_den, double eps,
+                              bool* singular, cd (&row)[C]) {
     cd w[C];
     bool ok = true;
     bool solved = false;
@@ -338,30 +371,28 @@ SM_HD int ip_row(Mat<C>& W, const Mat<C>& U, int n, double threshold, bool use_g
         // Edelman, Johnson) needs only the determinant, which the elimination for w = A^-1 e_n yields anyway: when that bound
         // is already under half the threshold the gate passes for certain and the inverse is never formed.  Everything else
         // (near the threshold, above it, singular, non-finite) takes the exact route below, so the decisions are unchanged.
-        double ad2 = 0.0;
-        const bool piv_ok = solve_unit(A, n, w, &ad2);
+        Mat<C> A;
+        make_A(A);
         double g = mat_fro2(A) / (double)C;   // (|A|_F^2 / C)^C
         double gc = g;
 #pragma unroll
         for (int i = 1; i < C; ++i) gc *= g;
+        double ad2 = 0.0;
+        const bool piv_ok = solve_unit_inplace(A, n, w, &ad2);
         solved = piv_ok && (4.0 * gc < 0.25 * threshold * threshold * ad2);
     }
     if (!solved) {
-        Mat<C> Ainv;
-        const bool inv_ok = mat_inverse(A, Ainv);
-        if (!inv_ok) {
+        Mat<C> Ax;          // the out-of-line call takes addresses: only these objects live in local memory
+        make_A(Ax);
+        cd wx[C];
+        const int r = ip_row_exact<C>(&Ax, n, threshold, use_gate, wx);
+        if (r < 0) {
             *singular = true;
             return 0;
         }
-        ok = use_gate ? cond_below(A, Ainv, inv_ok, threshold) : true;
-        // w = A^-1 e_n : column n of the inverse (compile-time indexed select)
+        ok = r == 1;
 #pragma unroll
-        for (int i = 0; i < C; ++i) {
-            w[i] = Ainv.a[i][0];
-#pragma unroll
-            for (int j = 1; j < C; ++j)
-                if (j == n) w[i] = Ainv.a[i][j];
-        }
+        for (int i = 0; i < C; ++i) w[i] = wx[i];
     }
     // q = w^H U w
     cd q = cd_make(0.0, 0.0);
@@ -374,16 +405,34 @@ SM_HD int ip_row(Mat<C>& W, const Mat<C>& U, int n, double threshold, bool use_g
     }
     cd den = cd_sqrt(q);
     if (floor_den && cd_less_real(den, eps)) den = cd_make(eps, 0.0);
+#pragma unroll
+    for (int j = 0; j < C; ++j) row[j] = cd_div(cd_conj(w[j]), den);
+    return ok ? 1 : 0;
+}
+
+template <int C>
+struct ProductOfRegisters {   // A = W U with both factors in registers (mat_mul)
+    const Mat<C>& W;
+    const Mat<C>& U;
+    SM_HD void operator()(Mat<C>& A) const { mat_mul(W, U, A); }
+};
+
+template <int C>
+SM_HD int ip_row(Mat<C>& W, const Mat<C>& U, int n, double threshold, bool use_gate, bool floor_den, double eps,
+                 bool* singular) {
+    cd row[C];
+    const ProductOfRegisters<C> make_A{W, U};
+    const int ok = ip_row_from_product<C>(make_A, U, n, threshold, use_gate, floor_den, eps, singular, row);
     if (ok) {
 #pragma unroll
         for (int r = 0; r < C; ++r) {
             if (r == n) {
 #pragma unroll
-                for (int j = 0; j < C; ++j) W.a[r][j] = cd_div(cd_conj(w[j]), den);
+                for (int j = 0; j < C; ++j) W.a[r][j] = row[j];
             }
         }
     }
-    return ok ? 1 : 0;
+    return ok;
 }
 
 // ------------------------------------------------------------------------------ Hermitian eigen / Riccati
