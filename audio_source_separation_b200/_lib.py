@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbssgpu.so')
+LIB_PATH = os.environ.get('BSSGPU_LIBRARY') or os.path.join(_HERE, 'libbssgpu.so')   # BSSGPU_LIBRARY: A/B against another build
 
 # enum bss_status
 OK, EINVAL, ECUDA, ESINGULAR, ENOMEM, ESTATE, EUNSUPPORTED, ENCCL = 0, -1, -2, -3, -4, -5, -6, -7

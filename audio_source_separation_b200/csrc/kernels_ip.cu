@@ -4,9 +4,6 @@
 //   - projection-back scale              src/algorithm/projection_back.py:12-21
 //   - log|det W|                         src/bss/ilrma.py:675
 //   - least-squares filter from (Y, X)   src/bss/ilrma.py:167-173
-#include <cstdlib>
-#include <cstring>
-
 #include "handle.h"
 #include "smallmat.cuh"
 
@@ -70,84 +67,6 @@ __global__ void __launch_bounds__(64) ip_sweep_kernel(const IpArgs a) {
         herm_unpack<C>(a.Cx + (size_t)idx * C * C, Cx);
 #pragma unroll 1
         for (int n = 0; n < C; ++n) a.pw[((size_t)b * C + n) * a.F + f] = row_power<C>(W, Cx, n);
-    }
-}
-
-// The same sweep with W in shared memory ([element][thread]: conflict-free 16-byte accesses) instead of registers: the live
-// set of a thread drops from W + U + A (192 fp64 registers' worth) to U + A, the kernel fits 168 registers without spilling
-// and six CTAs share an SM instead of four -- the sweep is bound by the latency of one thread's chain of row updates times
-// the number of waves, so occupancy is what pays.  Same operations in the same order as ip_sweep_kernel: identical results.
-template <int C>
-struct ProductOfShared {   // A = W U with W in shared memory as [element][64 threads], in the operation order of mat_mul
-    const cd* Ws;
-    int tid;
-    const Mat<C>& U;
-    __device__ __forceinline__ void operator()(Mat<C>& A) const {
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            cd wrow[C];
-#pragma unroll
-            for (int k = 0; k < C; ++k) wrow[k] = Ws[(i * C + k) * 64 + tid];
-#pragma unroll
-            for (int j = 0; j < C; ++j) {
-                cd s = cd_make(0.0, 0.0);
-#pragma unroll
-                for (int k = 0; k < C; ++k) cd_fma(s, wrow[k], U.a[k][j]);
-                A.a[i][j] = s;
-            }
-        }
-    }
-};
-
-template <int C, int REGS>
-__global__ void __maxnreg__(REGS) ip_sweep_ws_kernel(const IpArgs a) {
-    __shared__ cd Ws[C * C][64];
-    const int tid = threadIdx.x;
-    const long long idx = (long long)blockIdx.x * blockDim.x + tid;
-    if (idx >= (long long)a.B * a.F) return;
-    const int b = (int)(idx / a.F), f = (int)(idx - (long long)b * a.F);
-#pragma unroll
-    for (int e = 0; e < C * C; ++e) {
-        const double2 v = a.W[(size_t)idx * C * C + e];
-        Ws[e][tid] = cd_make(v.x, v.y);
-    }
-    bool singular = false;
-#pragma unroll 1
-    for (int n = 0; n < C; ++n) {
-        Mat<C> U;
-        herm_unpack<C>(a.U + (((size_t)b * C + n) * a.F + f) * C * C, U);
-        cd row[C];
-        const ProductOfShared<C> make_A{&Ws[0][0], tid, U};
-        const int ok = ip_row_from_product<C>(make_A, U, n, a.threshold, a.use_gate != 0, a.floor_den != 0, a.eps, &singular, row);
-        if (ok) {
-#pragma unroll
-            for (int j = 0; j < C; ++j) Ws[n * C + j][tid] = row[j];
-        }
-        if (a.gate) a.gate[((size_t)b * C + n) * a.F + f] = ok;
-    }
-    if (singular) atomicAdd(a.flags, 1);
-#pragma unroll
-    for (int e = 0; e < C * C; ++e) {
-        const cd v = Ws[e][tid];
-        a.W[(size_t)idx * C * C + e] = make_double2(v.x, v.y);
-        if (a.Wf) a.Wf[(size_t)idx * C * C + e] = cf_make((float)v.x, (float)v.y);
-    }
-    if (a.pw) {
-        Mat<C> Cx;
-        herm_unpack<C>(a.Cx + (size_t)idx * C * C, Cx);
-#pragma unroll 1
-        for (int n = 0; n < C; ++n) {
-            // p_n = w_n^H Cx w_n, the operation order of row_power
-            cd q = cd_make(0.0, 0.0);
-#pragma unroll
-            for (int i = 0; i < C; ++i) {
-                cd sacc = cd_make(0.0, 0.0);
-#pragma unroll
-                for (int j = 0; j < C; ++j) cd_fma(sacc, Cx.a[i][j], cd_conj(Ws[n * C + j][tid]));
-                cd_fma(q, Ws[n * C + i][tid], sacc);
-            }
-            a.pw[((size_t)b * C + n) * a.F + f] = q.x;
-        }
     }
 }
 
@@ -679,25 +598,9 @@ int launch_ip_t(bss_handle* h, const IpArgs& a, int32_t* order_out) {
         ip2_kernel<C><<<grid, threads, 0, h->stream>>>(a, order_out, a.eigval);
         h->last_ip_kernel = 4;
     } else if (per_thread) {
-        // C <= 4: W in shared memory, 200 registers (five CTAs of 64 threads per SM) or 168 (six); BSSGPU_IP_FORM = regs | ws168 |
-        // ws200 selects the form for A/B measurements
-        static const int form = [] {
-            const char* e = getenv("BSSGPU_IP_FORM");
-            if (!e) return 200;
-            if (!strcmp(e, "regs")) return 0;
-            if (!strcmp(e, "ws168")) return 168;
-            return 200;
-        }();
-        if constexpr (C <= 4) {
-            if (form == 0)
-                ip_sweep_kernel<C><<<grid, threads, 0, h->stream>>>(a);
-            else if (form == 168)
-                ip_sweep_ws_kernel<C, 168><<<grid, threads, 0, h->stream>>>(a);
-            else
-                ip_sweep_ws_kernel<C, 200><<<grid, threads, 0, h->stream>>>(a);
-        } else {
-            ip_sweep_kernel<C><<<grid, threads, 0, h->stream>>>(a);
-        }
+        // (keeping W in shared memory to raise the occupancy -- 200 or 168 registers, five or six CTAs per SM -- measured the
+        // same 124 - 126 us as this all-register form once the exact route had been moved out of line: profiles/round2_ab_ip_forms.md)
+        ip_sweep_kernel<C><<<grid, threads, 0, h->stream>>>(a);
         h->last_ip_kernel = 1;
     } else {
         h->last_ip_kernel = 2;

@@ -26,10 +26,38 @@ constexpr int FU_HEAD_BYTES = (FU_MAX_WARPS * FU_STAGES * 8 + 2 * FU_MAX_WARPS *
 struct FusedParams {
     MuArgs a;
     float* part;                  // [B][n_chunks][N][K][2][Tp] partial sums of the activation statistics
-    int pb_stride;                // bytes of a bin's filter rows Wf [C][C] complex64 (the second bulk copy of a stage)
+    const unsigned char* pbin;    // packed per-bin parameters: Wf [C][C] complex64 | T [N][K] float, pb_stride bytes per bin
+    int pb_stride;
     int n_chunks, bins_per_chunk, n_blocks;
     uint32_t stage_bytes, par_off;
 };
+
+// Packed per-bin parameters of the fused kernel: the bin's filter rows Wf [C][C] complex64 followed by its basis values
+// T [N][K] (160 bytes at C = 4, K = 2), so that both arrive in the ring stage with the bin's block by one bulk copy.
+// One thread per 16-byte piece: 8 pieces of filter (straight copies), then N K / 4 pieces gathered from [B][N][F][K].
+__global__ void __launch_bounds__(256) fused_pack_kernel(const cf* Wf, const float* basis, unsigned char* out, int B, int N, int C, int F,
+                                                         int K, int stride) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pieces = stride >> 4;
+    if (idx >= (long long)B * F * pieces) return;
+    const int q = (int)(idx % pieces);
+    const long long bf = idx / pieces;
+    const int f = (int)(bf % F), b = (int)(bf / F);
+    const int wq = C * C / 2;   // 16-byte pieces of the filter
+    float4 v;
+    if (q < wq) {
+        v = __ldg(reinterpret_cast<const float4*>(Wf + (size_t)bf * C * C) + q);
+    } else {
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = (q - wq) * 4 + j, n = i / K, k = i - n * K;
+            t[j] = i < N * K ? __ldg(basis + (((size_t)b * N + n) * F + f) * K + k) : 0.f;
+        }
+        v = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    reinterpret_cast<float4*>(out)[idx] = v;
+}
 
 __device__ __forceinline__ float2 rcp2f(float2 v) { return make_float2(rcp_fast(v.x), rcp_fast(v.y)); }
 
@@ -73,7 +101,7 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, MINB) mu_fused_kernel(const
     const uint32_t blk_bytes = (uint32_t)(C * L * 8);
     const size_t bin_bytes = (size_t)C * Tp * 8;
     const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.X) + ((size_t)b * a.F * C * Tp + (size_t)blk0 * C) * 8;
-    const unsigned char* par0 = reinterpret_cast<const unsigned char*>(a.Wf) + (size_t)b * a.F * p.pb_stride;   // filter rows of bin 0
+    const unsigned char* par0 = p.pbin + (size_t)b * a.F * p.pb_stride;
 
     // shared memory: [warps][STG] mbarriers | exchange[2][FU_MAX_WARPS][16] floats | [warps][STG] stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * FU_STAGES;
@@ -126,10 +154,6 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, MINB) mu_fused_kernel(const
 #pragma unroll
     for (int j = 0; j < 2; ++j) tts[j] = (2 * lane + 64 * j) < L ? 2 * lane + 64 * j : 0;
 
-    // old basis values: a.basis [B][N][F][K]; lane l < 8 walks the bins of (n, k) = (l / K, l % K)
-    const float* tsrc = a.basis + (((size_t)b * N + (lane < N * KC ? lane / KC : 0)) * a.F) * KC + (lane < N * KC ? lane % KC : 0);
-    float tcur = (lane < N * KC && f_begin < f_end) ? __ldg(tsrc + f_begin * KC) : 0.f;
-
     int cstage = 0;
     uint32_t cphase = 0;
 #pragma unroll 1
@@ -155,14 +179,12 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, MINB) mu_fused_kernel(const
         const unsigned char* stage = ring + (size_t)cstage * p.stage_bytes;
         const cf* xs = reinterpret_cast<const cf*>(stage);
         const float2* wf = reinterpret_cast<const float2*>(stage + p.par_off);
-        // basis row of this bin: lane l < 8 holds T[n = l / K][k = l % K] (fetched one bin ahead), every lane gets all eight
-        const float told = tcur;
-        if (lane < N * KC && f + 1 < f_end) tcur = __ldg(tsrc + (f + 1) * KC);
+        const float* tb = reinterpret_cast<const float*>(stage + p.par_off) + C * C * 2;
         float tk[N][KC];
 #pragma unroll
         for (int n = 0; n < N; ++n)
 #pragma unroll
-            for (int kk = 0; kk < KC; ++kk) tk[n][kk] = __shfl_sync(BSS_FULL, told, n * KC + kk);
+            for (int kk = 0; kk < KC; ++kk) tk[n][kk] = tb[n * KC + kk];
 
         // ---- source powers of this lane's frames, basis statistics with the old basis ---------------------------------
         // (no per-lane branches: lanes past the end of a ragged block read frame 0 instead; their activation values are
@@ -238,9 +260,11 @@ __global__ void __launch_bounds__(FU_MAX_WARPS * 32, MINB) mu_fused_kernel(const
                 dn += e0[g * 16 + 2 * lane + 1];
             }
             dn = fmaxf(dn, a.eps);
+            const float told = tb[lane];
             tnew = told * sqrtf(nm / dn);
             if (warp == 0) a.basis_out[(((size_t)b * N + lane / KC) * a.F + f) * KC + (lane % KC)] = tnew;
         }
+        __syncwarp();   // the last read of the stage (tb) is behind every lane: lane 0 may refill it at the top of the next bin
         float tn[N][KC];
 #pragma unroll
         for (int n = 0; n < N; ++n)
@@ -297,7 +321,7 @@ static int launch_mu_fused_t(bss_handle* h, const MuArgs& a, int* n_chunks_out, 
     p.a = a;
     p.n_blocks = n_blocks;
     const int blk_frames = a.Tp < BSS_XSLAB ? a.Tp : BSS_XSLAB;
-    p.pb_stride = C * C * 8;
+    p.pb_stride = round_up(C * C * 8 + C * KC * 4, 16);
     p.par_off = (uint32_t)round_up(C * blk_frames * 8, 16);
     p.stage_bytes = (uint32_t)round_up((int)p.par_off + p.pb_stride, 128);
     const size_t smem_bytes = (size_t)FU_HEAD_BYTES + (size_t)n_blocks * STG * p.stage_bytes;
@@ -335,7 +359,15 @@ static int launch_mu_fused_t(bss_handle* h, const MuArgs& a, int* n_chunks_out, 
         BSS_CUDA(h, cudaMalloc(&h->part, need * sizeof(float)));
         h->part_elems = need;
     }
+    const size_t pb_bytes = (size_t)a.B * a.F * p.pb_stride;
+    BSS_TRY(ensure_staging(h, pb_bytes));
+    p.pbin = (const unsigned char*)h->staging;
     p.part = h->part;
+    const long long pieces = (long long)a.B * a.F * (p.pb_stride >> 4);
+    fused_pack_kernel<<<(unsigned)cdiv(pieces, 256), 256, 0, h->stream>>>(a.Wf, a.basis, (unsigned char*)h->staging, a.B, C, C, a.F, KC,
+                                                                        p.pb_stride);
+    h->launches++;
+    BSS_CUDA(h, cudaGetLastError());
     mu_fused_kernel<C, KC, MINB><<<(unsigned)n_ctas, n_blocks * 32, smem_bytes, h->stream>>>(p);
     h->launches++;
     BSS_CUDA(h, cudaGetLastError());
