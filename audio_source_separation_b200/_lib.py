@@ -28,7 +28,7 @@ F32, F64, C64, C128, I32, I16 = 0, 1, 2, 3, 4, 5
 # enum bss_option / bss_info
 OPT_IP_KERNEL, OPT_ACT_CHUNKS, OPT_BLOCKING_SYNC, OPT_SOURCE_MODEL = 0, 1, 2, 3
 SOURCE_MODEL_AUTO, SOURCE_MODEL_THREE_PASS, SOURCE_MODEL_FUSED = 0, 1, 2
-IP_AUTO, IP_THREAD_PER_BIN, IP_LANE_GROUP, IP_FUSED, IP_PAIRWISE = 0, 1, 2, 3, 4
+IP_AUTO, IP_THREAD_PER_BIN, IP_LANE_GROUP, IP_PAIRWISE = 0, 1, 2, 4
 INFO_IP_KERNEL, INFO_GRAPH_REPLAYS, INFO_LAUNCHES, INFO_ACT_CHUNKS, INFO_SOURCE_MODEL = 0, 1, 2, 3, 4
 
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64,

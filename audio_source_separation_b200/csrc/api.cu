@@ -585,7 +585,7 @@ int bss_set_option(bss_handle* h, int option, int value) {
     if (!h) return BSS_EINVAL;
     switch (option) {
         case BSS_OPT_IP_KERNEL:
-            if (value < 0 || value > 3) return bss_fail(h, BSS_EINVAL, "BSS_OPT_IP_KERNEL takes 0 (auto), 1, 2 or 3");
+            if (value < 0 || value > 2) return bss_fail(h, BSS_EINVAL, "BSS_OPT_IP_KERNEL takes 0 (auto), 1 or 2");
             if (value != h->opt_ip_kernel) h->graph_sig = h->graph_rec_sig = 0;   // a kept graph recorded the other kernel
             h->opt_ip_kernel = value;
             return BSS_OK;

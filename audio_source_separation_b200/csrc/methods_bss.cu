@@ -81,7 +81,7 @@ IpArgs ip_args(bss_handle* h, bool want_power) {
     a.flags = h->flags;
     a.order = nullptr;
     a.eigval = nullptr;
-    a.variant = h->opt_ip_kernel == 3 ? 0 : h->opt_ip_kernel;
+    a.variant = h->opt_ip_kernel;
     a.B = h->B;
     a.F = h->F;
     a.C = h->C;

@@ -125,8 +125,7 @@ enum bss_state {
  * measurements can compare them. */
 enum bss_option {
     BSS_OPT_IP_KERNEL = 0,    /* iterative-projection sweep: 0 = choose by problem size (default), 1 = one thread per bin
-                                 (ip_sweep_kernel), 2 = lane group per bin (ip_sweep_group_kernel), 3 = in the epilogue of the
-                                 covariance kernel (no stand-alone launch; Gauss-ILRMA IP with n_channels <= 4 only)       */
+                                 (ip_sweep_kernel), 2 = lane group per bin (ip_sweep_group_kernel)                          */
     BSS_OPT_SOURCE_MODEL = 3, /* NMF source model of (t-)ILRMA: 0 = fused single-pass kernel where it covers the configuration
                                  (Gauss, domain 2, n_basis 2, 4 channels, n_frames <= 512), else three passes (default);
                                  1 = always three passes (basis kernel, power tiles, activation kernel); 2 = same as 0      */
