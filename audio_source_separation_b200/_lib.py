@@ -345,9 +345,31 @@ class NcclComm:
         ctypes.memmove(ctypes.byref(uid), box[0], 128)
         torch.cuda.set_device(device)
         comm = ctypes.c_void_p()
-        self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
-        self._nccl.ncclCommInitRank.restype = ctypes.c_int
-        rc = self._nccl.ncclCommInitRank(ctypes.byref(comm), self.world, uid, self.rank)
+        max_ctas = int(os.environ.get('BSSGPU_NCCL_MAX_CTAS', '0'))
+        rc = -1
+        if max_ctas > 0:
+            # ncclConfig_t as of NCCL 2.27 (newer libraries accept an older, shorter struct): cap the CTAs the collective's
+            # kernel may occupy, so that a gather running beside the update loops takes few SMs from them
+            class _Config(ctypes.Structure):
+                _fields_ = [('size', ctypes.c_size_t), ('magic', ctypes.c_uint), ('version', ctypes.c_uint), ('blocking', ctypes.c_int),
+                            ('cgaClusterSize', ctypes.c_int), ('minCTAs', ctypes.c_int), ('maxCTAs', ctypes.c_int),
+                            ('netName', ctypes.c_char_p), ('splitShare', ctypes.c_int), ('trafficClass', ctypes.c_int),
+                            ('commName', ctypes.c_char_p), ('collnetEnable', ctypes.c_int), ('CTAPolicy', ctypes.c_int),
+                            ('shrinkShare', ctypes.c_int), ('nvlsCTAs', ctypes.c_int)]
+            undef = -2 ** 31
+            cfg = _Config(ctypes.sizeof(_Config), 0xcafebeef, 22703, undef, undef, undef, max_ctas, None, undef, undef, None, undef, undef,
+                          undef, undef)
+            try:
+                fn = self._nccl.ncclCommInitRankConfig
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int, ctypes.POINTER(_Config)]
+                fn.restype = ctypes.c_int
+                rc = fn(ctypes.byref(comm), self.world, uid, self.rank, ctypes.byref(cfg))
+            except AttributeError:
+                rc = -1
+        if rc != 0:
+            self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
+            self._nccl.ncclCommInitRank.restype = ctypes.c_int
+            rc = self._nccl.ncclCommInitRank(ctypes.byref(comm), self.world, uid, self.rank)
         if rc != 0:
             raise RuntimeError("ncclCommInitRank failed ({})".format(rc))
         self.handle = comm

@@ -239,7 +239,7 @@ class BatchedGaussILRMA:
         return out if device_out is None else None
 
     def separate_waveform_batch_sharded(self, x, fft_size, hop_size=None, window_fn='hann', iteration=100, basis=None, activation=None,
-                                        group=None, pipeline='ramp', loss_out=None):
+                                        group=None, pipeline='ramp', loss_out=None, overlap_gather=True):
         """BASELINE configs[4] as one call, time domain in / time domain out (one process per GPU, torch.distributed
         initialised by the caller; without it: one GPU, no collective).  Every rank passes the SAME global description --
         x (B,C,n_samples) float32/float64 in host memory, of which it reads only its own contiguous shard
@@ -287,6 +287,8 @@ class BatchedGaussILRMA:
         self.gather_backend = 'bss_gather_outputs' if comm is not None else 'torch.distributed.all_gather'
 
         def gather_part(i, plo, phi):
+            if not overlap_gather:
+                return
             if comm is not None:
                 h = self._parts[i][1]
                 h.gather_outputs(comm, y_local[plo:phi].data_ptr(), y_all.data_ptr() + plo * row_bytes, (phi - plo) * row_bytes,
@@ -300,6 +302,11 @@ class BatchedGaussILRMA:
                                      activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
                                      device_out=y_local.data_ptr(), loss_out=loss_out if loss_out is not None else np.zeros(Bl),
                                      on_done=gather_part)
+        if not overlap_gather:     # one collective after the last sub-batch (measurement aid: nothing overlaps it)
+            if comm is not None:
+                self._parts[0][1].gather_outputs(comm, y_local.data_ptr(), y_all.data_ptr(), Bl * row_bytes, Bl * row_bytes)
+            else:
+                dist.all_gather_into_tensor(y_all, y_local.clone(), group=group)
         if comm is not None:
             for slot in self._parts:    # the gathers were queued on the sub-batch streams
                 if slot is not None:

@@ -17,10 +17,12 @@ static thread_local std::string g_create_error;
 namespace {
 typedef int (*nccl_group_fn)(void);
 typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*nccl_err_fn)(int);
 struct NcclApi {
     nccl_group_fn group_start = nullptr, group_end = nullptr;
     nccl_bcast_fn broadcast = nullptr;
+    nccl_allgather_fn all_gather = nullptr;
     nccl_err_fn error_string = nullptr;
     bool ok = false;
 };
@@ -34,8 +36,9 @@ const NcclApi& nccl_api() {
         a.group_start = (nccl_group_fn)dlsym(lib, "ncclGroupStart");
         a.group_end = (nccl_group_fn)dlsym(lib, "ncclGroupEnd");
         a.broadcast = (nccl_bcast_fn)dlsym(lib, "ncclBroadcast");
+        a.all_gather = (nccl_allgather_fn)dlsym(lib, "ncclAllGather");
         a.error_string = (nccl_err_fn)dlsym(lib, "ncclGetErrorString");
-        a.ok = a.group_start && a.group_end && a.broadcast;
+        a.ok = a.group_start && a.group_end && a.broadcast && a.all_gather;
         return a;
     }();
     return api;
@@ -572,13 +575,25 @@ int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, co
         if (rc == 0) return BSS_OK;
         return bss_fail(h, BSS_ENCCL, std::string(what) + ": " + (nccl.error_string ? nccl.error_string(rc) : "NCCL error"));
     };
-    BSS_TRY(check(nccl.group_start(), "ncclGroupStart"));
-    int rc = 0;
-    for (int r = 0; r < n_ranks && rc == 0; ++r)
-        rc = nccl.broadcast(send_device, (char*)recv_base_device + (size_t)r * rank_stride_bytes, bytes, /*ncclInt8*/ 0, r, nccl_comm, h->stream);
-    const int rc_end = nccl.group_end();
-    BSS_TRY(check(rc, "ncclBroadcast"));
-    return check(rc_end, "ncclGroupEnd");
+    // One ncclAllGather (the bandwidth-efficient collective) into a rank-major scratch buffer, then one strided device copy
+    // into the final places; when the final places are rank-major already, straight into them.  BSSGPU_GATHER=bcast selects
+    // the copy-free form, a group of broadcasts, for A/B measurements.
+    static const bool by_broadcast = getenv("BSSGPU_GATHER") && !strcmp(getenv("BSSGPU_GATHER"), "bcast");
+    if (by_broadcast) {
+        BSS_TRY(check(nccl.group_start(), "ncclGroupStart"));
+        int rc = 0;
+        for (int r = 0; r < n_ranks && rc == 0; ++r)
+            rc = nccl.broadcast(send_device, (char*)recv_base_device + (size_t)r * rank_stride_bytes, bytes, /*ncclInt8*/ 0, r, nccl_comm, h->stream);
+        const int rc_end = nccl.group_end();
+        BSS_TRY(check(rc, "ncclBroadcast"));
+        return check(rc_end, "ncclGroupEnd");
+    }
+    if (rank_stride_bytes == bytes) return check(nccl.all_gather(send_device, recv_base_device, bytes, 0, nccl_comm, h->stream), "ncclAllGather");
+    BSS_TRY(ensure_scratch2(h, (size_t)n_ranks * bytes));
+    BSS_TRY(check(nccl.all_gather(send_device, h->scratch2, bytes, 0, nccl_comm, h->stream), "ncclAllGather"));
+    BSS_CUDA(h, cudaMemcpy2DAsync(recv_base_device, rank_stride_bytes, h->scratch2, bytes, bytes, (size_t)n_ranks, cudaMemcpyDeviceToDevice,
+                                  h->stream));
+    return BSS_OK;
 }
 
 int bss_set_option(bss_handle* h, int option, int value) {

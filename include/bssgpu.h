@@ -236,8 +236,9 @@ int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int f
                                  int apply_projection_back);
 /* The one collective of a sharded batch (BASELINE configs[4]: "NVLink gather only at end"): every rank contributes `bytes`
  * bytes at send_device and receives rank r's contribution at recv_base_device + r * rank_stride_bytes (r = 0 .. n_ranks-1,
- * its own included), on the handle's stream, as one NCCL group of broadcasts -- so a sub-batch can be gathered straight into
- * its final place of a (global batch, ...) buffer while later sub-batches are still iterating.  `nccl_comm` is an
+ * its own included), on the handle's stream: one ncclAllGather (through a rank-major scratch buffer and one strided device copy
+ * when rank_stride_bytes != bytes) -- so a sub-batch can be gathered into its final place of a (global batch, ...) buffer
+ * while later sub-batches are still iterating.  `nccl_comm` is an
  * ncclComm_t of n_ranks ranks created by the caller (libnccl.so.2 is resolved at run time, the library does not link it).
  * Every rank must call it in the same order.  No reference counterpart (the reference has no batch axis). */
 int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, const void* send_device, void* recv_base_device,
