@@ -26,7 +26,7 @@ F32, F64, C64, C128, I32, I16 = 0, 1, 2, 3, 4, 5
 (STATE_DEMIX_FILTER, STATE_ESTIMATION, STATE_BASIS, STATE_ACTIVATION, STATE_LATENT, STATE_DIAGONALIZER,
  STATE_SPATIAL, STATE_TARGET, STATE_COVARIANCE, STATE_GATE, STATE_VARIANCE, STATE_ORDER, STATE_EIGVAL) = range(13)
 # enum bss_option / bss_info
-OPT_IP_KERNEL, OPT_ACT_CHUNKS, OPT_BLOCKING_SYNC, OPT_SOURCE_MODEL = 0, 1, 2, 3
+OPT_IP_KERNEL, OPT_ACT_CHUNKS, OPT_BLOCKING_SYNC, OPT_SOURCE_MODEL, OPT_ASYNC_INPUT = 0, 1, 2, 3, 4
 SOURCE_MODEL_AUTO, SOURCE_MODEL_THREE_PASS, SOURCE_MODEL_FUSED = 0, 1, 2
 IP_AUTO, IP_THREAD_PER_BIN, IP_LANE_GROUP, IP_PAIRWISE = 0, 1, 2, 4
 INFO_IP_KERNEL, INFO_GRAPH_REPLAYS, INFO_LAUNCHES, INFO_ACT_CHUNKS, INFO_SOURCE_MODEL = 0, 1, 2, 3, 4
@@ -74,6 +74,11 @@ SIGNATURES = {
     'bss_separate_waveform': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     'bss_separate_waveform_device': (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     'bss_gather_outputs': (_i, [_vp, _vp, _i, _i, _vp, _vp, ctypes.c_size_t, ctypes.c_size_t]),
+    'bss_peer_alloc': (_i, [_i, ctypes.c_size_t, ctypes.POINTER(_vp), _vp]),
+    'bss_peer_open': (_i, [_i, _vp, ctypes.POINTER(_vp)]),
+    'bss_peer_close': (_i, [_i, _vp]),
+    'bss_peer_free': (_i, [_i, _vp]),
+    'bss_push_outputs': (_i, [_vp, _i, _i, ctypes.POINTER(_vp), _vp, ctypes.c_size_t, ctypes.c_size_t]),
     'bss_compute_demix_filter': (_i, [_vp]),
     'bss_set_option': (_i, [_vp, _i, _i]),
     'bss_get_info': (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64)]),
@@ -280,6 +285,11 @@ class Handle:
     def compute_demix_filter(self):
         self._check(self._lib.bss_compute_demix_filter(self._h))
 
+    def push_outputs(self, peers, send_ptr, dst_offset_bytes, nbytes):
+        """Copy `nbytes` from send_ptr into every peer's result buffer (a `PeerBuffers`) at dst_offset_bytes, on the handle's stream."""
+        self._check(self._lib.bss_push_outputs(self._h, peers.world, peers.rank, peers.bases, ctypes.c_void_p(send_ptr),
+                                               int(dst_offset_bytes), int(nbytes)))
+
     def gather_outputs(self, comm, send_ptr, recv_base_ptr, nbytes, rank_stride_bytes):
         """All-gather on the handle's stream over `comm` (an `NcclComm`): rank r's `nbytes` land at recv_base + r * stride."""
         self._check(self._lib.bss_gather_outputs(self._h, comm.handle, comm.world, comm.rank, ctypes.c_void_p(send_ptr),
@@ -309,6 +319,63 @@ class Handle:
 
     def launch_count(self):
         return int(self._lib.bss_launch_count(self._h))
+
+
+class PeerBuffers:
+    """One result buffer per rank of a node, each allocated by its owner (`bss_peer_alloc`) and mapped into every other
+    process through CUDA IPC (`bss_peer_open`), so that a rank can push its outputs straight into its peers' buffers with
+    device-to-device copies over NVLink.  The 64-byte handles travel through the caller's torch.distributed group."""
+
+    def __init__(self, rank, world, device, nbytes, group=None):
+        import torch.distributed as dist
+        lib = load()
+        self.rank, self.world, self.device, self.nbytes = int(rank), int(world), int(device), int(nbytes)
+        self.own = ctypes.c_void_p()
+        self._opened = []
+        handle = (ctypes.c_ubyte * 64)()
+        code = lib.bss_peer_alloc(self.device, self.nbytes, ctypes.byref(self.own), handle)
+        if code != OK:
+            self.own = ctypes.c_void_p()
+        handles = [None] * self.world
+        # every rank takes part in the exchange, also one whose allocation failed (it sends None and all ranks give up together)
+        dist.all_gather_object(handles, bytes(handle) if code == OK else None, group=group)
+        if any(hd is None for hd in handles):
+            self.close()
+            raise RuntimeError("bss_peer_alloc failed on rank(s) {}".format([r for r, hd in enumerate(handles) if hd is None]))
+        self.bases = (ctypes.c_void_p * self.world)()
+        self.bases[self.rank] = self.own.value
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            code = lib.bss_peer_open(self.device, buf, ctypes.byref(p))
+            if code != OK:
+                raise RuntimeError("bss_peer_open failed for rank {} ({})".format(r, code))
+            self.bases[r] = p.value
+            self._opened.append(p)
+
+    def as_tensor(self, shape, dtype):
+        """The rank's own buffer as a torch tensor (shares the memory; keep this object alive while the tensor is used)."""
+        import torch
+        typestr = {torch.float32: '<f4', torch.float64: '<f8'}[dtype]
+        holder = type('DevicePointer', (), {})()
+        holder.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(self.own.value), False), 'version': 2}
+        holder.owner = self
+        return torch.as_tensor(holder, device=torch.device('cuda', self.device))
+
+    def unmap(self):
+        """Drop this process's mappings of the peers' buffers (before their owners free them)."""
+        lib = load()
+        for p in getattr(self, '_opened', []):
+            lib.bss_peer_close(self.device, p)
+        self._opened = []
+
+    def close(self):
+        self.unmap()
+        if getattr(self, 'own', None) is not None and self.own.value:
+            load().bss_peer_free(self.device, self.own)
+            self.own = ctypes.c_void_p()
 
 
 class NcclComm:

@@ -6,6 +6,8 @@ are identical to B separate `GaussILRMA` runs.  `shard_range` / `gather_outputs`
 ranks of a torch.distributed job (one process per GPU); the only communication is the final all-gather of
 the separated outputs over NCCL.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -111,8 +113,14 @@ class BatchedGaussILRMA:
                     slot[1].close()
             self._parts = [None] * n_parts
 
+        import threading
         import time
         t_start = time.perf_counter()
+        # Inputs go up in index order: the host link carries one copy at a time, and the sub-batch whose input arrives first
+        # is the one whose update loop can start (and whose outputs can leave) first.  Left to race, the host threads put the
+        # large middle sub-batches last at 8 GPUs per node -- their small state uploads queue behind the other threads' input
+        # copies -- and most of the batch then finishes together at the very end (profiles/round2_scaling.md).
+        fed = [threading.Event() for _ in spans]
         marks = [dict(size=hi - lo) for lo, hi in spans]
         self.timeline = marks   # per sub-batch: ms since the start of the call at which each phase returned to the host
 
@@ -131,14 +139,21 @@ class BatchedGaussILRMA:
                 # several host threads per GPU (and several processes per node) wait on their streams at the same time:
                 # sleep instead of spinning, the threads that still have launches to issue need the cores
                 h.set_option(_lib.OPT_BLOCKING_SYNC, 1 if n_parts > 1 else 0)
+                # the input copy is only queued by `feed` (the caller's arrays live until this call returns, and it returns
+                # after every sub-batch has drained): the copies of all sub-batches go over the host link back to back
+                h.set_option(_lib.OPT_ASYNC_INPUT, 1)
                 self._parts[i] = slot = (key, h)
             h = slot[1]
-            # small uploads first: queued behind the other sub-batches' input copies they would wait for all of them
-            h.reset_spatial()
-            h.set_state(_lib.STATE_BASIS, basis[lo:hi], np.float64)
-            h.set_state(_lib.STATE_ACTIVATION, activation[lo:hi], np.float64)
-            marks[i]['state'] = round(1e3 * (time.perf_counter() - t_start), 2)
-            feed(h, lo, hi)
+            try:
+                h.reset_spatial()
+                h.set_state(_lib.STATE_BASIS, basis[lo:hi], np.float64)
+                h.set_state(_lib.STATE_ACTIVATION, activation[lo:hi], np.float64)
+                marks[i]['state'] = round(1e3 * (time.perf_counter() - t_start), 2)
+                if i > 0:
+                    fed[i - 1].wait()
+                feed(h, lo, hi)     # queues the input copy (+ STFT) on the sub-batch's stream
+            finally:
+                fed[i].set()
             marks[i]['input'] = round(1e3 * (time.perf_counter() - t_start), 2)
             h.run(iteration)
             marks[i]['queued'] = round(1e3 * (time.perf_counter() - t_start), 2)
@@ -151,8 +166,14 @@ class BatchedGaussILRMA:
             if on_done is not None:
                 on_done(0, *spans[0])
         else:
+            def guarded(i):
+                try:
+                    return job(i)
+                finally:
+                    fed[i].set()    # also when the sub-batch failed before its upload: the next one must not wait for ever
+
             with ThreadPoolExecutor(max_workers=n_parts) as pool:
-                futures = [pool.submit(job, i) for i in range(n_parts)]
+                futures = [pool.submit(guarded, i) for i in range(n_parts)]
                 for i, fut in enumerate(futures):
                     fut.result()
                     if on_done is not None:
@@ -245,9 +266,12 @@ class BatchedGaussILRMA:
         x (B,C,n_samples) float32/float64 in host memory, of which it reads only its own contiguous shard
         `shard_range(B, rank, world)` -- uploads its shard pipelined against the update loop (STFT, `iteration` updates,
         projection back and ISTFT on the device), leaves its separated signals on its GPU and takes part in the one
-        collective of the path: the NCCL all-gather of the separated outputs over NVLink.  Returns a torch tensor
-        (B,N,n_out) of x's dtype on this rank's GPU with the signals of ALL mixtures in batch order.  `loss_out` (B_local,)
-        float64 receives the final losses of this rank's mixtures (the job's device-to-host read)."""
+        exchange of the path: the all-gather of the separated outputs over NVLink -- by default pushed into the peers' result
+        buffers through peer memory (`bss_push_outputs`), with BSSGPU_GATHER_MODE=nccl the NCCL collective
+        (`bss_gather_outputs`).  Returns a torch tensor (B,N,n_out) of x's dtype on this rank's GPU with the signals of ALL
+        mixtures in batch order; in the peer-memory form it is a view of a buffer the model keeps and the next job on ANY
+        rank overwrites.  `loss_out` (B_local,) float64 receives the final losses of this rank's mixtures (the job's
+        device-to-host read)."""
         import torch
         import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -280,9 +304,36 @@ class BatchedGaussILRMA:
         # broadcasts on the sub-batch handle's own stream, straight into the final places) over a communicator of our own;
         # torch.distributed's all_gather serves when that communicator cannot be created.
         Bl = hi - lo
+        esize = 8 if tdtype == torch.float64 else 4
+        row_bytes = C * n_out * esize
+        mode = os.environ.get('BSSGPU_GATHER_MODE', 'push')
+        peers = self._peer_buffers(rank, world, group, B * row_bytes) if mode == 'push' else None
+        if peers is not None:
+            # peer-memory form: the result buffers of all ranks are mapped into every process (CUDA IPC) and each rank pushes
+            # a finished sub-batch straight into its peers' buffers with device-to-device copies over NVLink -- copy engines,
+            # so the update loops of the later sub-batches keep every SM (an NCCL kernel beside them does not overlap:
+            # profiles/round2_scaling.md).  The buffers are reused by the next job: a barrier on entry keeps a fast rank
+            # from writing into a buffer its owner is still reading, one on exit says that every push has landed.
+            self.gather_backend = 'bss_push_outputs'
+            dist.barrier(group=group)
+            y_all = peers.as_tensor((B, C, n_out), tdtype)
+            y_local = y_all[lo:hi]
+
+            def push_part(i, plo, phi):
+                self._parts[i][1].push_outputs(peers, y_local[plo:phi].data_ptr(), (lo + plo) * row_bytes, (phi - plo) * row_bytes)
+
+            self.separate_waveform_batch(xl, fft_size, hop_size, window_fn, iteration=iteration,
+                                         basis=None if basis is None else basis[lo:hi],
+                                         activation=None if activation is None else activation[lo:hi], pipeline=pipeline,
+                                         device_out=y_local.data_ptr(), loss_out=loss_out if loss_out is not None else np.zeros(Bl),
+                                         on_done=push_part)
+            for slot in self._parts:    # the pushes were queued on the sub-batch streams
+                if slot is not None:
+                    slot[1].synchronize()
+            dist.barrier(group=group)
+            return y_all
         y_all = torch.empty((B, C, n_out), dtype=tdtype, device=device)
         y_local = y_all[lo:hi]
-        row_bytes = C * n_out * y_all.element_size()
         comm = self._own_comm(rank, world, group)
         self.gather_backend = 'bss_gather_outputs' if comm is not None else 'torch.distributed.all_gather'
 
@@ -312,6 +363,35 @@ class BatchedGaussILRMA:
                 if slot is not None:
                     slot[1].synchronize()
         return y_all
+
+    def _peer_buffers(self, rank, world, group, nbytes):
+        """The job's result buffers for the peer-memory gather, kept for the model's lifetime and grown on demand (None when
+        CUDA IPC cannot be set up between the ranks; every rank then agrees on the NCCL gather through one small all-reduce)."""
+        import torch
+        import torch.distributed as dist
+        cached = getattr(self, '_peers', None)
+        if cached is not None and cached[0] == (rank, world) and (cached[1] is None or cached[1].nbytes >= nbytes):
+            return cached[1]
+        if cached is not None and cached[1] is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)     # nobody is still pushing into the buffers about to be released
+            cached[1].unmap()
+            dist.barrier(group=group)     # ... and nobody still maps the buffer its owner frees
+            cached[1].close()
+        peers = None
+        self.gather_backend_error = None
+        try:
+            peers = _lib.PeerBuffers(rank, world, self.device, nbytes, group=group)
+        except Exception as exc:   # reported through gather_backend / gather_backend_error; the NCCL gather serves
+            self.gather_backend_error = "{}: {}".format(type(exc).__name__, exc)
+        ok = torch.tensor([1 if peers is not None else 0], device=torch.device('cuda', self.device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if peers is not None:
+                peers.close()
+            peers = None
+        self._peers = ((rank, world), peers)
+        return peers
 
     def _own_comm(self, rank, world, group):
         """NCCL communicator for `bss_gather_outputs`, created once per model (None when NCCL cannot be set up that way; every

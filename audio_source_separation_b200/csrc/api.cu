@@ -288,8 +288,8 @@ static int finish_input(bss_handle* h) {
     h->y_valid = false;
     // ISS carries estimates instead of a filter: (re)derive them when the filter came first
     if (h->cfg.spatial == BSS_SPATIAL_ISS && h->cfg.method != BSS_FAST_MNMF && h->has_filter) BSS_TRY(bss_refresh_estimates(h));
-    // the caller's buffer may be reused as soon as we return
-    BSS_CUDA(h, bss_wait(h));
+    // the caller's buffer may be reused as soon as we return (BSS_OPT_ASYNC_INPUT: the caller keeps it until the next wait)
+    if (!h->opt_async_input) BSS_CUDA(h, bss_wait(h));
     return BSS_OK;
 }
 
@@ -575,11 +575,11 @@ int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, co
         if (rc == 0) return BSS_OK;
         return bss_fail(h, BSS_ENCCL, std::string(what) + ": " + (nccl.error_string ? nccl.error_string(rc) : "NCCL error"));
     };
-    // One ncclAllGather (the bandwidth-efficient collective) into a rank-major scratch buffer, then one strided device copy
-    // into the final places; when the final places are rank-major already, straight into them.  BSSGPU_GATHER=bcast selects
-    // the copy-free form, a group of broadcasts, for A/B measurements.
-    static const bool by_broadcast = getenv("BSSGPU_GATHER") && !strcmp(getenv("BSSGPU_GATHER"), "bcast");
-    if (by_broadcast) {
+    // One NCCL group of broadcasts, each rank's contribution straight into its final place (no staging copy).
+    // BSSGPU_GATHER=allgather selects the other form for A/B measurements: one ncclAllGather into a rank-major scratch buffer
+    // plus one strided device copy -- measured slower inside the 8-GPU job (64.0 against 60.6 ms, profiles/round2_scaling.md).
+    static const bool by_allgather = getenv("BSSGPU_GATHER") && !strcmp(getenv("BSSGPU_GATHER"), "allgather");
+    if (!by_allgather || n_ranks == 1) {
         BSS_TRY(check(nccl.group_start(), "ncclGroupStart"));
         int rc = 0;
         for (int r = 0; r < n_ranks && rc == 0; ++r)
@@ -593,6 +593,66 @@ int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, co
     BSS_TRY(check(nccl.all_gather(send_device, h->scratch2, bytes, 0, nccl_comm, h->stream), "ncclAllGather"));
     BSS_CUDA(h, cudaMemcpy2DAsync(recv_base_device, rank_stride_bytes, h->scratch2, bytes, bytes, (size_t)n_ranks, cudaMemcpyDeviceToDevice,
                                   h->stream));
+    return BSS_OK;
+}
+
+int bss_peer_alloc(int device, size_t bytes, void** dptr, void* ipc_handle_64) {
+    if (!dptr || !ipc_handle_64 || bytes == 0) return BSS_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (cudaSetDevice(device) != cudaSuccess) return BSS_ECUDA;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return BSS_ENOMEM;
+    }
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, p) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+        return BSS_ECUDA;
+    }
+    memcpy(ipc_handle_64, &hd, 64);
+    *dptr = p;
+    return BSS_OK;
+}
+
+int bss_peer_open(int device, const void* ipc_handle_64, void** dptr) {
+    if (!dptr || !ipc_handle_64) return BSS_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return BSS_ECUDA;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle_64, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return BSS_ECUDA;
+    }
+    *dptr = p;
+    return BSS_OK;
+}
+
+int bss_peer_close(int device, void* dptr) {
+    if (!dptr) return BSS_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return BSS_ECUDA;
+    return cudaIpcCloseMemHandle(dptr) == cudaSuccess ? BSS_OK : BSS_ECUDA;
+}
+
+int bss_peer_free(int device, void* dptr) {
+    if (!dptr) return BSS_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return BSS_ECUDA;
+    return cudaFree(dptr) == cudaSuccess ? BSS_OK : BSS_ECUDA;
+}
+
+int bss_push_outputs(bss_handle* h, int n_ranks, int rank, void* const* peer_bases, const void* send_device, size_t dst_offset_bytes,
+                     size_t bytes) {
+    if (!h || !peer_bases || !send_device || n_ranks < 1 || rank < 0 || rank >= n_ranks) return BSS_EINVAL;
+    BSS_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (bytes == 0) return BSS_OK;
+    // start with the next rank: at any moment the ranks write to different peers
+    for (int i = 1; i < n_ranks; ++i) {
+        const int r = (rank + i) % n_ranks;
+        if (!peer_bases[r]) return bss_fail(h, BSS_EINVAL, "push: a peer buffer is not mapped");
+        BSS_CUDA(h, cudaMemcpyAsync((char*)peer_bases[r] + dst_offset_bytes, send_device, bytes, cudaMemcpyDefault, h->stream));
+    }
     return BSS_OK;
 }
 
@@ -611,6 +671,9 @@ int bss_set_option(bss_handle* h, int option, int value) {
             return BSS_OK;
         case BSS_OPT_BLOCKING_SYNC:
             h->opt_blocking_sync = value != 0;
+            return BSS_OK;
+        case BSS_OPT_ASYNC_INPUT:
+            h->opt_async_input = value != 0;
             return BSS_OK;
         case BSS_OPT_ACT_CHUNKS:
             if (value < 0) return bss_fail(h, BSS_EINVAL, "BSS_OPT_ACT_CHUNKS takes 0 (auto) or a positive count");

@@ -63,6 +63,7 @@ struct bss_handle {
     int opt_source_model = 0;      // BSS_OPT_SOURCE_MODEL
     int last_source_model = 0;     // BSS_INFO_SOURCE_MODEL
     int opt_blocking_sync = 0;     // BSS_OPT_BLOCKING_SYNC
+    int opt_async_input = 0;       // BSS_OPT_ASYNC_INPUT
     cudaEvent_t ev_block = nullptr;
     int opt_act_chunks = 0;        // BSS_OPT_ACT_CHUNKS
     int last_act_chunks = 0;       // BSS_INFO_ACT_CHUNKS

@@ -131,6 +131,11 @@ enum bss_option {
                                  1 = always three passes (basis kernel, power tiles, activation kernel); 2 = same as 0      */
     BSS_OPT_BLOCKING_SYNC = 2,/* 1: host waits of this handle sleep on a blocking CUDA event instead of spinning in
                                  cudaStreamSynchronize (for many host threads / processes per node); 0 = spin (default) */
+    BSS_OPT_ASYNC_INPUT = 4,  /* 1: bss_set_input / bss_set_input_waveform return as soon as the copy is queued on the handle's
+                                 stream; the caller keeps the (pinned) buffer untouched until the next call that waits for
+                                 the handle (bss_synchronize, bss_loss, ...).  0 = they return when the buffer may be
+                                 reused (default).  A pipelined job queues the inputs of all its sub-batches back to back
+                                 this way, so the host link never idles behind a sub-batch's STFT                          */
     BSS_OPT_ACT_CHUNKS = 1    /* number of bin chunks of the cross-bin (activation) reduction of the source model; 0 = chosen
                                  from batch size and machine (default).  The chunking fixes the summation order, so a single
                                  mixture given the chunk count of a batch reproduces the batch bit for bit                */
@@ -243,6 +248,19 @@ int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int f
  * Every rank must call it in the same order.  No reference counterpart (the reference has no batch axis). */
 int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, const void* send_device, void* recv_base_device,
                        size_t bytes, size_t rank_stride_bytes);
+/* The same gather without a collective kernel: every rank pushes its contribution into the result buffers of all its peers
+ * with device-to-device copies over NVLink (copy engines: no SM is taken from the update loops of the other sub-batches, which
+ * is what a gather that overlaps them needs -- an NCCL kernel beside them measured no gain, profiles/round2_scaling.md).
+ * The result buffers are allocated by bss_peer_alloc (cudaMalloc + CUDA IPC handle, 64 bytes, which the caller hands to the
+ * other processes), mapped by bss_peer_open in every peer, and all have the same layout: bss_push_outputs copies `bytes`
+ * bytes from send_device to peer_bases[r] + dst_offset_bytes for every r != rank on the handle's stream.  The caller
+ * synchronises its streams and then all ranks (a barrier) before anybody reads. */
+int bss_peer_alloc(int device, size_t bytes, void** dptr, void* ipc_handle_64);
+int bss_peer_open(int device, const void* ipc_handle_64, void** dptr);
+int bss_peer_close(int device, void* dptr);
+int bss_peer_free(int device, void* dptr);
+int bss_push_outputs(bss_handle* h, int n_ranks, int rank, void* const* peer_bases, const void* send_device, size_t dst_offset_bytes,
+                     size_t bytes);
 /* ISS keeps no filter: W = Y X^H (X X^H)^-1 (src/bss/ilrma.py:167-173); result is readable as
  * BSS_STATE_DEMIX_FILTER afterwards */
 int bss_compute_demix_filter(bss_handle* h);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """The sharded waveform job alone (BASELINE configs[4] as one call) under torchrun: median seconds of three jobs, max over ranks.
-   Variants through the environment: BSSGPU_GATHER=bcast, BSSGPU_NCCL_MAX_CTAS=n, PROBE_OVERLAP=0 (one gather at the end)."""
+   Variants through the environment: BSSGPU_GATHER_MODE=push|nccl, BSSGPU_GATHER=allgather, BSSGPU_NCCL_MAX_CTAS=n,
+   PROBE_OVERLAP=0 (one NCCL gather at the end)."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,7 +51,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"world": world, "seconds": round(float(t.item()), 5), "it_per_s": round(world * B * steps / float(t.item())),
-                      "gather": os.environ.get('BSSGPU_GATHER', 'allgather'), "max_ctas": os.environ.get('BSSGPU_NCCL_MAX_CTAS'),
+                      "mode": os.environ.get('BSSGPU_GATHER_MODE', 'push'), "gather": os.environ.get('BSSGPU_GATHER', 'bcast'), "max_ctas": os.environ.get('BSSGPU_NCCL_MAX_CTAS'),
                       "overlap": overlap, "backend": getattr(m, 'gather_backend', None), "timeline_rank0": m.timeline}))
 if world > 1:
     dist.barrier()
