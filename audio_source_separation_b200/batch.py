@@ -393,6 +393,27 @@ class BatchedGaussILRMA:
         self._peers = ((rank, world), peers)
         return peers
 
+    def close(self, group=None):
+        """Release what the whole-job calls keep between jobs: the sub-batch handles, and -- collectively, every rank calls it
+        -- the peer-mapped result buffers and the communicator of the sharded job.  Tensors returned by the peer-memory form
+        of `separate_waveform_batch_sharded` are invalid afterwards."""
+        import torch.distributed as dist
+        for slot in getattr(self, '_parts', []):
+            if slot is not None:
+                slot[1].close()
+        self._parts = []
+        peers = getattr(self, '_peers', None)
+        if peers is not None and peers[1] is not None:
+            dist.barrier(group=group)      # nobody still pushes into the buffers
+            peers[1].unmap()
+            dist.barrier(group=group)      # nobody still maps the buffer its owner frees
+            peers[1].close()
+        self._peers = None
+        comm = getattr(self, '_comm', None)
+        if comm is not None and comm[1] is not None:
+            comm[1].close()
+        self._comm = None
+
     def _own_comm(self, rank, world, group):
         """NCCL communicator for `bss_gather_outputs`, created once per model (None when NCCL cannot be set up that way; every
         rank then agrees on the fallback through one small all-reduce)."""

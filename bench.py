@@ -15,7 +15,7 @@ SAME synthetic mixtures: `mix2(4, 2049, 512, seed)` of SURVEY.md Appendix D, com
   e2e          BASELINE configs[4] through the public host API, host<->device copies inside the timed region:
                BatchedGaussILRMA.separate_waveform_batch_sharded -- the rank's waveforms up from pinned host memory, STFT +
                K iterations + projection back + ISTFT on the device, the separated signals of all ranks gathered over
-               NVLink onto every GPU (the one collective of the path; none at N = 1), the final losses down.
+               NVLink onto every GPU (the one exchange of the path, peer-memory pushes; none at N = 1), the final losses down.
                `e2e_host_waveform` / `e2e_host_spectrogram` deliver the outputs to pinned host memory instead (waveforms or
                STFT tensors both ways): those are bound by the host link of the box, not by the GPUs
   roofline     the covariance-accumulate kernel timed alone (CUDA events) against the measured HBM peak
@@ -660,7 +660,9 @@ def run_gpu_arm(args):
     if tuple(holder['y'].shape) != (world * B, C, n_out) or not np.all(np.isfinite(losses)):
         raise RuntimeError("sharded job: wrong output shape or non-finite loss")
     timelines["sharded"] = getattr(shard_model, 'timeline', None)
+    gather_backend = (getattr(shard_model, 'gather_backend', None), getattr(shard_model, 'gather_backend_error', None))
     holder.clear()
+    shard_model.close()     # collective at N > 1: the peer-mapped result buffers go back before the gather microbenchmark
     del shard_model
 
     # the all-gather alone, warm: (world - 1) x the per-rank outputs received per GPU
@@ -738,9 +740,10 @@ def run_gpu_arm(args):
                        "storage": "complex64/float32 tensors, float64 per-bin solves",
                        "e2e_job": "BASELINE configs[4] as one call, BatchedGaussILRMA.separate_waveform_batch_sharded (pipelined "
                                   "sub-batches: {}): H2D of the rank's int16 PCM waveforms ({} samples x 4ch per mixture) from pinned memory + "
-                                  "STFT ({}/{}) + {} iterations + separate/projection-back + ISTFT on the device + NCCL all-gather of all "
-                                  "separated float32 signals onto every GPU, sub-batch by sub-batch behind the update loops of the later "
-                                  "ones (N = 1: no collective, the signals stay on the GPU) + D2H of the "
+                                  "STFT ({}/{}) + {} iterations + separate/projection-back + ISTFT on the device + all-gather of all "
+                                  "separated float32 signals onto every GPU over NVLink (pushed into the peers' result buffers through "
+                                  "peer memory, bss_push_outputs; BSSGPU_GATHER_MODE=nccl: NCCL broadcasts), sub-batch by sub-batch "
+                                  "behind the update loops of the later ones (N = 1: no exchange, the signals stay on the GPU) + D2H of the "
                                   "final per-mixture losses; bytes amortised per iteration.  e2e_host_* are the same job with the "
                                   "outputs delivered to pinned host memory instead (bound by the host link of the box, see "
                                   "profiles/r6d_pcie_probe_8gpu.json)".format(pipeline, n_samples, FFT, HOP, steps)},
@@ -748,7 +751,8 @@ def run_gpu_arm(args):
             "e2e": {"value": world * B * steps / shard_s, "unit": "iterations/s", "h2d_bytes_per_step": wave_h2d / steps,
                     "d2h_bytes_per_step": B * 8 / steps, "seconds": shard_s, "seconds_per_job": [round(v, 6) for v in shard_runs],
                     "job": "separate_waveform_batch_sharded: waveforms up, separated waveforms gathered over NVLink onto every GPU, "
-                           "losses down"},
+                           "losses down",
+                    "gather_backend": gather_backend[0] if world > 1 else None, "gather_backend_error": gather_backend[1]},
             "e2e_host_waveform": {"value": world * B * steps / wave_s, "unit": "iterations/s", "h2d_bytes_per_step": wave_h2d / steps,
                                   "d2h_bytes_per_step": wave_d2h / steps, "seconds": wave_s, "seconds_per_job": [round(v, 6) for v in wave_runs],
                                   "job": "separate_waveform_batch: waveforms up, separated waveforms down to pinned host memory"},
