@@ -236,14 +236,15 @@ int bss_separate_waveform(bss_handle* h, void* y, int dtype, int fft_size, int h
 int bss_set_option(bss_handle* h, int option, int value);
 int bss_get_info(bss_handle* h, int what, int64_t* value);
 /* the same with the time-domain estimates left on the device: y_device (B,N,bss_istft_length(...)) float32/float64; queued on
- * the handle's stream (bss_synchronize before another stream reads it) -- feeds the NCCL gather of a sharded batch */
+ * the handle's stream (bss_synchronize before another stream reads it) -- feeds the exchange of a sharded batch */
 int bss_separate_waveform_device(bss_handle* h, void* y_device, int dtype, int fft_size, int hop_size, const double* window,
                                  int apply_projection_back);
 /* The one collective of a sharded batch (BASELINE configs[4]: "NVLink gather only at end"): every rank contributes `bytes`
  * bytes at send_device and receives rank r's contribution at recv_base_device + r * rank_stride_bytes (r = 0 .. n_ranks-1,
- * its own included), on the handle's stream: one ncclAllGather (through a rank-major scratch buffer and one strided device copy
- * when rank_stride_bytes != bytes) -- so a sub-batch can be gathered into its final place of a (global batch, ...) buffer
- * while later sub-batches are still iterating.  `nccl_comm` is an
+ * its own included), on the handle's stream: one NCCL group of broadcasts, each contribution straight into its final place
+ * (BSSGPU_GATHER=allgather in the environment: one ncclAllGather through a rank-major scratch buffer and one strided device
+ * copy instead) -- so a sub-batch can be gathered into its final place of a (global batch, ...) buffer while later
+ * sub-batches are still iterating.  `nccl_comm` is an
  * ncclComm_t of n_ranks ranks created by the caller (libnccl.so.2 is resolved at run time, the library does not link it).
  * Every rank must call it in the same order.  No reference counterpart (the reference has no batch axis). */
 int bss_gather_outputs(bss_handle* h, void* nccl_comm, int n_ranks, int rank, const void* send_device, void* recv_base_device,
