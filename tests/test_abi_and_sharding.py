@@ -188,3 +188,89 @@ def test_batched_public_surface_is_complete():
                  'separate_waveform_batch_sharded', 'separate_waveforms', 'update_once', 'compute_negative_loglikelihood',
                  'demix_filter', 'basis', 'activation'):
         assert hasattr(BatchedGaussILRMA, name), name
+
+
+class _RecordingHandle:
+    """Stand-in for `_lib.Handle` that records the order of the calls the pipelined driver makes (no device)."""
+    log = []
+    fail_on_size = None
+
+    def __init__(self, **cfg):
+        self.size = cfg['n_batch']
+        self.priority = cfg['stream_priority']
+        if self.size == _RecordingHandle.fail_on_size:
+            raise RuntimeError("no device for a sub-batch of {}".format(self.size))
+
+    def set_option(self, option, value):
+        _RecordingHandle.log.append(('option', self.size, option, value))
+
+    def reset_spatial(self):
+        pass
+
+    def set_state(self, which, value, dtype):
+        import time
+        time.sleep(0.002 * self.size)      # larger sub-batches are slower here, as on the host link: they would upload last
+
+    def run(self, n):
+        _RecordingHandle.log.append(('run', self.size, n))
+
+    def launch_count(self):
+        return 0
+
+    def close(self):
+        pass
+
+
+def _pipelined_model(monkeypatch):
+    from audio_source_separation_b200 import _lib, batch
+    monkeypatch.setattr(_lib, 'Handle', _RecordingHandle)
+    _RecordingHandle.log = []
+    _RecordingHandle.fail_on_size = None
+    model = batch.BatchedGaussILRMA.__new__(batch.BatchedGaussILRMA)
+    model.n_basis, model.device, model.algorithm_spatial, model.normalize = 2, 0, 'IP', 'power'
+    model.reference_id, model.domain, model.eps, model.threshold = 0, 2, 1e-12, 1e-12
+    return model
+
+
+def test_pipelined_job_uploads_inputs_in_sub_batch_order(monkeypatch):
+    """`_pipelined` (profiles/round2_scaling.md): whatever the host threads' pace, the inputs go up in sub-batch order, every
+    sub-batch asks for queued (not awaited) input copies, earlier sub-batches get the higher stream priority, and `on_done`
+    is called in order on the calling thread."""
+    import threading
+    from audio_source_separation_b200 import _lib
+    model = _pipelined_model(monkeypatch)
+    sizes = [3, 1, 4, 2, 1]
+    B, C, F, T = sum(sizes), 2, 5, 6
+    fed, drained, done = [], [], []
+    caller = threading.get_ident()
+
+    def on_done(i, lo, hi):
+        assert threading.get_ident() == caller
+        done.append((i, lo, hi))
+
+    model._pipelined(B, C, F, T, 7, np.zeros((B, C, F, 2)), np.zeros((B, C, 2, T)), sizes,
+                     lambda h, lo, hi: fed.append((lo, hi)), lambda h, lo, hi: drained.append((lo, hi)), on_done=on_done)
+    edges = np.concatenate(([0], np.cumsum(sizes)))
+    spans = [(int(edges[i]), int(edges[i + 1])) for i in range(len(sizes))]
+    assert fed == spans
+    assert sorted(drained) == spans
+    assert done == [(i,) + spans[i] for i in range(len(sizes))]
+    assert [e for e in _RecordingHandle.log if e[0] == 'run'] and all(e[2] == 7 for e in _RecordingHandle.log if e[0] == 'run')
+    asked = {(e[1], e[2]): e[3] for e in _RecordingHandle.log if e[0] == 'option'}
+    assert all(asked[(n, _lib.OPT_ASYNC_INPUT)] == 1 and asked[(n, _lib.OPT_BLOCKING_SYNC)] == 1 for n in set(sizes))
+    priorities = [slot[1].priority for slot in model._parts]
+    assert priorities == sorted(priorities) and priorities[-1] == 0      # CUDA: lower number = higher priority
+    assert [m['size'] for m in model.timeline] == sizes and all('out' in m for m in model.timeline)
+
+
+def test_pipelined_job_does_not_hang_when_a_sub_batch_fails(monkeypatch):
+    """A sub-batch that fails before its upload releases the next one's wait; the error reaches the caller."""
+    model = _pipelined_model(monkeypatch)
+    _RecordingHandle.fail_on_size = 4
+    sizes = [2, 4, 3]
+    B, C, F, T = sum(sizes), 2, 5, 6
+    fed = []
+    with pytest.raises(RuntimeError, match="no device for a sub-batch of 4"):
+        model._pipelined(B, C, F, T, 3, np.zeros((B, C, F, 2)), np.zeros((B, C, 2, T)), sizes,
+                         lambda h, lo, hi: fed.append((lo, hi)), lambda h, lo, hi: None)
+    assert fed == [(0, 2), (6, 9)]
