@@ -400,6 +400,9 @@ class BatchedGaussILRMA:
         -- the peer-mapped result buffers and the communicator of the sharded job.  Tensors returned by the peer-memory form
         of `separate_waveform_batch_sharded` are invalid afterwards."""
         import torch.distributed as dist
+        if self.handle is not None:
+            self.handle.close()
+            self.handle, self._key = None, None
         for slot in getattr(self, '_parts', []):
             if slot is not None:
                 slot[1].close()
