@@ -452,7 +452,7 @@ def bench_configs(device, peak):
     h.set_state(_lib.STATE_ACTIVATION, V0[np.newaxis], np.float64)
     b4 = 8 * M * F * T4 + 8 * M * F * M * M + 4 * (M * 2 * (F + T4) + M * F * M)
     out['cfg4'] = {"what": "FastMNMF 8ch x 2049 bins x 1024 frames, K=2, N=8, 50 iterations per call", "ms_per_iter": timed_loop(h, 50, 3),
-                   "roofline": cov_roofline(h, b4, 20, "mnmf weights + cov_mma_kernel<8> (all 8 weighted covariances of update_diagonalizer)"),
+                   "roofline": cov_roofline(h, b4, 20, "cov8_kernel (all 8 weighted covariances of update_diagonalizer, inverse variances computed in the kernel)"),
                    "note": "143.4 MB algorithmic per launch; weights are not credited (SURVEY section 8d)"}
     h.close()
     return out
