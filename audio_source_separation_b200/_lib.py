@@ -377,6 +377,12 @@ class PeerBuffers:
             load().bss_peer_free(self.device, self.own)
             self.own = ctypes.c_void_p()
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class NcclComm:
     """An NCCL communicator of our own for `bss_gather_outputs` (one per process / GPU), created through the same

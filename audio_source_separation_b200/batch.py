@@ -262,7 +262,7 @@ class BatchedGaussILRMA:
         return out if device_out is None else None
 
     def separate_waveform_batch_sharded(self, x, fft_size, hop_size=None, window_fn='hann', iteration=100, basis=None, activation=None,
-                                        group=None, pipeline='ramp', loss_out=None, overlap_gather=True):
+                                        group=None, pipeline='ramp', loss_out=None, overlap_gather=True, copy=False):
         """BASELINE configs[4] as one call, time domain in / time domain out (one process per GPU, torch.distributed
         initialised by the caller; without it: one GPU, no collective).  Every rank passes the SAME global description --
         x (B,C,n_samples) float32/float64 in host memory, of which it reads only its own contiguous shard
@@ -272,7 +272,7 @@ class BatchedGaussILRMA:
         buffers through peer memory (`bss_push_outputs`), with BSSGPU_GATHER_MODE=nccl the NCCL collective
         (`bss_gather_outputs`).  Returns a torch tensor (B,N,n_out) of x's dtype on this rank's GPU with the signals of ALL
         mixtures in batch order; in the peer-memory form it is a view of a buffer the model keeps and the next job on ANY
-        rank overwrites.  `loss_out` (B_local,) float64 receives the final losses of this rank's mixtures (the job's
+        rank overwrites (`copy=True` returns a tensor of its own instead, one device-to-device copy).  `loss_out` (B_local,) float64 receives the final losses of this rank's mixtures (the job's
         device-to-host read)."""
         import torch
         import torch.distributed as dist
@@ -333,7 +333,7 @@ class BatchedGaussILRMA:
                 if slot is not None:
                     slot[1].synchronize()
             dist.barrier(group=group)
-            return y_all
+            return y_all.clone() if copy else y_all
         y_all = torch.empty((B, C, n_out), dtype=tdtype, device=device)
         y_local = y_all[lo:hi]
         comm = self._own_comm(rank, world, group)
