@@ -274,3 +274,10 @@ def test_pipelined_job_does_not_hang_when_a_sub_batch_fails(monkeypatch):
         model._pipelined(B, C, F, T, 3, np.zeros((B, C, F, 2)), np.zeros((B, C, 2, T)), sizes,
                          lambda h, lo, hi: fed.append((lo, hi)), lambda h, lo, hi: None)
     assert fed == [(0, 2), (6, 9)]
+
+
+def test_every_entry_point_is_described_in_integration_md():
+    """INTEGRATION.md section 3 names, for every symbol of include/bssgpu.h, the reference code it replaces (or says that
+    there is none)."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    assert [s for s in _declared_symbols() if s not in doc] == []
