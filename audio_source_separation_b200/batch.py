@@ -25,6 +25,13 @@ def _check_presets(B, C, F, T, K, demix_filter=None, basis=None, activation=None
             raise ValueError("{} has shape {}, expected {}".format(name, tuple(np.shape(value)), shape))
 
 
+def _flag_device(device, group):
+    """Where the one-element agreement tensors of the sharded job live: on the GPU, in host memory for gloo groups."""
+    import torch
+    import torch.distributed as dist
+    return torch.device('cpu') if str(dist.get_backend(group)) == 'gloo' else torch.device('cuda', device)
+
+
 class BatchedGaussILRMA:
     def __init__(self, n_basis=10, domain=2, normalize='power', algorithm_spatial='IP', reference_id=0, eps=EPS,
                  threshold=THRESHOLD, device=0):
@@ -386,7 +393,7 @@ class BatchedGaussILRMA:
             peers = _lib.PeerBuffers(rank, world, self.device, nbytes, group=group)
         except Exception as exc:   # reported through gather_backend / gather_backend_error; the NCCL gather serves
             self.gather_backend_error = "{}: {}".format(type(exc).__name__, exc)
-        ok = torch.tensor([1 if peers is not None else 0], device=torch.device('cuda', self.device))
+        ok = torch.tensor([1 if peers is not None else 0], device=_flag_device(self.device, group))
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
             if peers is not None:
@@ -428,13 +435,15 @@ class BatchedGaussILRMA:
         if cached is not None and cached[0] == (rank, world):
             return cached[1]
         comm = None
-        self.gather_backend_error = None
+        earlier = getattr(self, 'gather_backend_error', None)     # why the peer-memory form was not taken, if it was tried
         try:
+            if str(dist.get_backend(group)) == 'gloo':
+                raise RuntimeError("gloo group: no NCCL communicator is made beside it")
             comm = _lib.NcclComm(rank, world, self.device, group=group)
         except Exception as exc:   # reported through gather_backend / gather_backend_error; the torch collective serves
-            self.gather_backend_error = "{}: {}".format(type(exc).__name__, exc)
+            self.gather_backend_error = "{}{}: {}".format(earlier + " | " if earlier else "", type(exc).__name__, exc)
             comm = None
-        ok = torch.tensor([1 if comm is not None else 0], device=torch.device('cuda', self.device))
+        ok = torch.tensor([1 if comm is not None else 0], device=_flag_device(self.device, group))
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
             if comm is not None:
